@@ -1,0 +1,152 @@
+/*
+ * pymfb.h - C ABI of libpymfb.so: the B200-native NMF multiplicative-update engine.
+ *
+ * The reference (nils-werner/pymf) has no FFI / plugin registry: its boundary for this
+ * path is the Python class pymf.NMF (pymf/nmf.py:23-202).  This header is the thin
+ * C layer a binding for that class sits on; `pymf_b200/nmf.py` is that binding
+ * (ctypes).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions cross the ABI.
+ *   - every function returns 0 on success, non-zero on failure;
+ *     pymfb_last_error() returns a thread-local message for the last failure.
+ *   - one context per GPU, one CUDA stream per context, a context is not re-entrant.
+ *   - matrices are row-major.  X is d x n_local (features x samples, pymf/nmf.py:34),
+ *     W is d x k (:42), H is k x n_local (:43).  With more than one rank, X and H are
+ *     block-sharded by COLUMNS; W is replicated.
+ *   - dtype codes: PYMFB_F32 = 0, PYMFB_F64 = 1.  The device computes in fp32 storage
+ *     (3xTF32 tensor-core products with fp32 accumulation, fp64 scalar combines).
+ */
+#ifndef PYMFB_H
+#define PYMFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pymfb_ctx pymfb_ctx;
+
+#define PYMFB_F32 0
+#define PYMFB_F64 1
+
+/* pymfb_run flags == keyword arguments of NMF.factorize (pymf/nmf.py:141-142) */
+#define PYMFB_COMPUTE_W   1u   /* compute_w   (:183-184) */
+#define PYMFB_COMPUTE_H   2u   /* compute_h   (:186-187) */
+#define PYMFB_COMPUTE_ERR 4u   /* compute_err (:189-190) */
+#define PYMFB_EARLY_STOP  8u   /* the `i > 1 and converged(i)` break (:198-202) */
+
+/* kernel-path selection (pymfb_set_option PYMFB_OPT_PATH) */
+#define PYMFB_PATH_AUTO 0      /* tcgen05 kernels when the shape allows, else SIMT */
+#define PYMFB_PATH_SIMT 1      /* fp32 CUDA-core kernels (exact fp32 FMA) */
+#define PYMFB_PATH_TC   2      /* tcgen05 3xTF32 kernels; error if the shape is unsupported */
+
+#define PYMFB_OPT_PATH 1
+
+/* Library / ABI version (major*1000 + minor). */
+int pymfb_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* pymfb_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is no driver / GPU); never fails. */
+int pymfb_device_count(void);
+
+/*
+ * Create an engine for a d x n_local shard of a d x n_global problem with k bases.
+ * Replaces NMF.__init__ (pymf/nmf.py:71-97).  col0 = global index of the shard's first
+ * column (only used by the synthetic generator).  Allocates W, H, the packed
+ * [X H^T | H H^T] reduction buffers and scratch on `device`.
+ */
+int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_t n_global,
+                 int64_t col0, int k);
+int pymfb_destroy(pymfb_ctx* ctx);
+
+int pymfb_set_option(pymfb_ctx* ctx, int option, int64_t value);
+
+/*
+ * Multi-GPU (one process per GPU).  Rank 0 calls pymfb_comm_unique_id (128 bytes, an
+ * ncclUniqueId), the host layer broadcasts it, every rank calls pymfb_comm_init.
+ * After that pymfb_prepare / pymfb_run sum the packed [X H^T | H H^T] partials (and
+ * ||X||^2) over ranks with one NCCL all-reduce per iteration on the context's stream.
+ * No counterpart in the reference (it is single-process).
+ */
+int pymfb_comm_unique_id(void* out128);
+int pymfb_comm_init(pymfb_ctx* ctx, const void* uid128, int world, int rank);
+
+/*
+ * Data residency - replaces `self.data = data` (pymf/nmf.py:93) and the `data[:,:]`
+ * full reads (:110,125,131).
+ *   bind_x    borrow a device pointer (fp32, row-major, leading dimension ld elements,
+ *             ld % 4 == 0, 16-byte aligned); the caller keeps it alive.
+ *   upload_x  copy a host matrix (fp32 or fp64, leading dimension ld elements) into a
+ *             context-owned fp32 device copy through a pinned, double-buffered staging ring.
+ *   gen_x     fill the context-owned X with the synthetic U[0,1) generator
+ *             (element (r, c) = hash(seed, r*n_global + col0 + c), see oracle/nmf_oracle.py).
+ */
+int pymfb_bind_x(pymfb_ctx* ctx, const float* x_dev, int64_t ld);
+int pymfb_upload_x(pymfb_ctx* ctx, const void* x_host, int dtype, int64_t ld);
+int pymfb_gen_x(pymfb_ctx* ctx, uint64_t seed);
+
+/*
+ * Factor access - the .W / .H attributes (pymf/nmf.py:42-43,116-120,173-177).
+ * Host pointers are dense row-major d x k / k x n_local of the given dtype.
+ * gen_w / gen_h fill from the synthetic generator (W: element (r,c)=hash(seed, r*k+c);
+ * H: hash(seed, r*n_global + col0 + c)).
+ */
+int pymfb_set_w(pymfb_ctx* ctx, const void* w_host, int dtype);
+int pymfb_set_h(pymfb_ctx* ctx, const void* h_host, int dtype);
+int pymfb_get_w(pymfb_ctx* ctx, void* w_host, int dtype);
+int pymfb_get_h(pymfb_ctx* ctx, void* h_host, int dtype);
+int pymfb_gen_w(pymfb_ctx* ctx, uint64_t seed);
+int pymfb_gen_h(pymfb_ctx* ctx, uint64_t seed);
+
+/*
+ * Run `niter` iterations of the factorize() loop (pymf/nmf.py:182-202): per iteration
+ * update_w (:128-132), then update_h (:122-126), then frobenius_norm (:100-114) and
+ * converged (:134-139), selected by `flags`.  ferr_host (niter doubles, may be NULL
+ * unless PYMFB_COMPUTE_ERR) receives the per-iteration errors; *n_iter_done the
+ * number of iterations executed and *n_ferr the number of valid ferr entries
+ * (n_iter_done - 1 after an early stop, because the reference drops entry i, :201).
+ * One host synchronisation at the end; the stop decision is taken on the device.
+ */
+int pymfb_run(pymfb_ctx* ctx, int niter, unsigned flags, double* ferr_host,
+              int* n_iter_done, int* n_ferr);
+
+/* ||X - W H||_F for the current factors (pymf/nmf.py:100-114), trace identity, fp64 combine. */
+int pymfb_frobenius(pymfb_ctx* ctx, double* out);
+
+/* Enqueue-only variant for benchmarking: enqueue niter iterations on the context's
+ * stream without synchronising (no early stop read-back).  pymfb_sync waits. */
+int pymfb_enqueue(pymfb_ctx* ctx, int niter, unsigned flags);
+int pymfb_sync(pymfb_ctx* ctx);
+
+/* The context's CUDA stream (cudaStream_t) so callers can record events on it. */
+void* pymfb_stream(pymfb_ctx* ctx);
+
+/* Timing helpers on the context's stream (CUDA events): returns elapsed ms. */
+int pymfb_event_create(void** ev);
+int pymfb_event_record(pymfb_ctx* ctx, void* ev);
+int pymfb_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);
+int pymfb_event_destroy(void* ev);
+
+/* Average device time (ms) of the dominant streaming kernel(s) over the launches since
+ * the last pymfb_kernel_timing_reset, measured with CUDA events on the launch stream
+ * when timing is enabled (enable = 1).  which: 0 = H-update pass, 1 = X H^T pass. */
+int pymfb_kernel_timing(pymfb_ctx* ctx, int enable);
+int pymfb_kernel_timing_read(pymfb_ctx* ctx, int which, double* avg_ms, int64_t* launches);
+
+/* Kernel launches issued by this context so far (all kernels of this library). */
+int64_t pymfb_launch_count(pymfb_ctx* ctx);
+
+/* Which path the context resolved to for its shape: PYMFB_PATH_SIMT or PYMFB_PATH_TC. */
+int pymfb_active_path(pymfb_ctx* ctx);
+
+/* Write a buffer larger than L2 (flush between timed iterations of small problems). */
+int pymfb_flush_l2(pymfb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMFB_H */

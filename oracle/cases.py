@@ -1,0 +1,53 @@
+"""Seeded parity cases shared by make_golden.py, the tests, smoke() and bench.py.
+
+TEST INFRASTRUCTURE ONLY.  ``build(name)`` regenerates (X, W0, H0) from the
+recipe; the matching reference outputs live in tests/golden/traj_<name>.npz.
+"""
+import numpy as np
+
+from .nmf_oracle import gen_matrix
+
+REF_TEST_SEED = 400401          # tests/test_pymf.py:32
+REF_TEST_INIT_SEED = 1234       # seed set right before the lazy W/H init in our fixtures
+
+
+def ref_test_matrix():
+    """tests/test_pymf.py:32-33."""
+    np.random.seed(REF_TEST_SEED)
+    return np.random.random((3, 50)) + 2.0
+
+
+# kind "np":   X = np.random.random (float64) after np.random.seed(seed); W0 then H0 follow
+#              from the same stream (SURVEY 8d, cfg1 recipe).
+# kind "hash": X/W0/H0 from the counter hash (float32 values), seeds seed, seed+1, seed+2 -
+#              the generator the device implements for the big synthetic configs.
+CASES = {
+    # BASELINE.json configs[0]
+    "cfg1": dict(kind="np", seed=0, d=1000, n=500, k=10, niter=100, keep=[1, 10, 50, 100]),
+    # ragged / odd shapes, nothing a multiple of anything
+    "ragged": dict(kind="np", seed=7, d=37, n=201, k=5, niter=30, keep=[1, 2, 30]),
+    "tiny": dict(kind="np", seed=11, d=3, n=7, k=2, niter=10, keep=[1, 10]),
+    "k1": dict(kind="np", seed=13, d=50, n=64, k=1, niter=5, keep=[5]),
+    # column prefix of cfg2 (d=4096, k=32) with the device generator
+    "cfg2_prefix": dict(kind="hash", seed=1234, d=4096, n=2048, k=32, niter=5, keep=[1, 5],
+                        store32=True),
+    # k = 128 (cfg3's k), tensor-path shape, small n/d
+    "k128": dict(kind="hash", seed=77, d=512, n=640, k=128, niter=5, keep=[1, 5], store32=True),
+    # k not a multiple of 16, d not a multiple of 128
+    "k40": dict(kind="hash", seed=99, d=300, n=1000, k=40, niter=8, keep=[1, 8], store32=True),
+}
+
+
+def build(name):
+    c = CASES[name]
+    d, n, k = c["d"], c["n"], c["k"]
+    if c["kind"] == "np":
+        np.random.seed(c["seed"])
+        X = np.random.random((d, n))
+        W0 = np.random.random((d, k))
+        H0 = np.random.random((k, n))
+    else:
+        X = gen_matrix(c["seed"], d, n)
+        W0 = gen_matrix(c["seed"] + 1, d, k).astype(np.float64)
+        H0 = gen_matrix(c["seed"] + 2, k, n).astype(np.float64)
+    return X, W0, H0

@@ -1,0 +1,89 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/pymf/nmf.py, loaded by path - see ref_loader.py).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no
+reference checkout):   python -m oracle.make_golden
+
+Each fixture stores the seeds/recipe that regenerate the inputs plus the
+reference's outputs (W, H, ferr), so the fixtures stay small.  Inputs are
+rebuilt by ``oracle.cases`` from the recipe at test time.
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import cases
+from .ref_loader import load_reference_nmf
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def run_steps(ref, X, W0, H0, k, niter, keep):
+    """Single-step the reference (factorize(niter=1) never triggers the early stop,
+    SURVEY 3.4) and record ferr per iteration and W/H at the iterations in keep."""
+    m = ref.NMF(X, num_bases=k)
+    m.W = W0.copy()
+    m.H = H0.copy()
+    ferr = np.zeros(niter)
+    normW = np.zeros(niter)
+    normH = np.zeros(niter)
+    snaps = {}
+    for i in range(niter):
+        m.factorize(niter=1)
+        ferr[i] = m.ferr[0]
+        normW[i] = np.linalg.norm(m.W)
+        normH[i] = np.linalg.norm(m.H)
+        if (i + 1) in keep:
+            snaps["W_%d" % (i + 1)] = m.W.copy()
+            snaps["H_%d" % (i + 1)] = m.H.copy()
+    return ferr, normW, normH, snaps
+
+
+def main():
+    ref = load_reference_nmf()
+    if ref is None:
+        sys.exit("no reference checkout found (set PYMF_REF)")
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- 1. the reference's own test case (tests/test_pymf.py:32-33,69,84-95) ----
+    A = cases.ref_test_matrix()
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    m = ref.NMF(A, num_bases=4)
+    m.factorize(niter=20)                       # lazy init: W then H from np.random
+    out = {"W_20": m.W.copy(), "H_20": m.H.copy(), "ferr_20": m.ferr.copy()}
+    m.factorize(compute_h=False)                # :92
+    out.update(W_a=m.W.copy(), H_a=m.H.copy(), ferr_a=m.ferr.copy())
+    m.factorize(compute_w=False)                # :93
+    out.update(W_b=m.W.copy(), H_b=m.H.copy(), ferr_b=m.ferr.copy())
+    m.factorize(compute_err=False)              # :94 (ferr untouched)
+    out.update(W_c=m.W.copy(), H_c=m.H.copy(), ferr_c=m.ferr.copy())
+    m.factorize(niter=20)                       # :95 warm start
+    out.update(W_d=m.W.copy(), H_d=m.H.copy(), ferr_d=m.ferr.copy())
+    np.savez(os.path.join(OUT, "ref_test_3x50.npz"), **out)
+    assert out["ferr_20"][-1] / 53 < 0.1
+
+    # ---- 2. early stop / truncation on the same matrix ----
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    m = ref.NMF(A, num_bases=4)
+    m.factorize(niter=100000)
+    np.savez(os.path.join(OUT, "ref_conv_3x50.npz"), W=m.W.copy(), H=m.H.copy(),
+             ferr_len=np.int64(len(m.ferr)), ferr_tail=m.ferr[-8:].copy(),
+             ferr_head=m.ferr[:8].copy())
+    print("early stop: len(ferr) =", len(m.ferr))
+
+    # ---- 3. trajectories on the parity cases ----
+    for name, c in cases.CASES.items():
+        if not c.get("golden", True):
+            continue
+        X, W0, H0 = cases.build(name)
+        ferr, nW, nH, snaps = run_steps(ref, X.astype(np.float64), W0, H0, c["k"], c["niter"],
+                                        set(c["keep"]))
+        if c.get("store32", False):
+            snaps = {k_: v.astype(np.float32) for k_, v in snaps.items()}
+        np.savez(os.path.join(OUT, "traj_%s.npz" % name), ferr=ferr, normW=nW, normH=nH, **snaps)
+        print(name, "ferr", ferr[0], "->", ferr[-1])
+
+
+if __name__ == "__main__":
+    main()

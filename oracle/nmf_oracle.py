@@ -1,0 +1,113 @@
+"""CPU oracle: numpy restatement of pymf's NMF multiplicative-update path.
+
+TEST INFRASTRUCTURE ONLY.  The product (``pymf_b200``) never imports this file;
+it is the checker for the CUDA path and the "port" CPU baseline of ``bench.py``.
+
+Pinning: the reference's own tests hold no golden vectors for this path
+(``tests/test_pymf.py:69,86-88`` is a loose smoke bound).  The oracle is therefore
+pinned against outputs of the reference itself: ``oracle/make_golden.py`` runs the
+unmodified ``/root/reference/pymf/nmf.py`` (loaded by path, see ``ref_loader.py``)
+and commits its trajectories under ``tests/golden/``; ``tests/test_oracle.py``
+requires this restatement to reproduce them to 1e-12 relative.
+
+Every function cites the reference lines it follows (paths relative to the
+reference checkout).  float64 throughout, same operation order as the reference.
+"""
+import numpy as np
+
+EPS_DENOM = 10 ** -9          # pymf/nmf.py:124,130 (added to the denominator only)
+EPS_CONV = 10 ** -8           # pymf/nmf.py:69  (NMF._EPS, convergence threshold)
+SENTINEL = -123456            # pymf/nmf.py:112
+
+
+def update_h(X, W, H):
+    """In-place H update.  pymf/nmf.py:122-126."""
+    H2 = np.dot(np.dot(W.T, W), H) + EPS_DENOM      # :124
+    H *= np.dot(W.T, X)                             # :125
+    H /= H2                                         # :126
+    return H
+
+
+def update_w(X, W, H):
+    """In-place W update (uses the H from before this iteration).  pymf/nmf.py:128-132."""
+    W2 = np.dot(np.dot(W, H), H.T) + EPS_DENOM      # :130
+    W *= np.dot(X, H.T)                             # :131
+    W /= W2                                         # :132
+    return W
+
+
+def frobenius_norm(X, W, H):
+    """||X - W H||_F.  pymf/nmf.py:100-114 (dense branch, :110)."""
+    return np.sqrt(np.sum((X - np.dot(W, H)) ** 2))
+
+
+def converged(ferr, i, num_samples):
+    """pymf/nmf.py:134-139."""
+    derr = np.abs(ferr[i] - ferr[i - 1]) / num_samples
+    return bool(derr < EPS_CONV)
+
+
+def init_wh(d, n, k):
+    """Lazy initialisation order of factorize(): W first, then H, from numpy's
+    global RNG.  pymf/nmf.py:116-120,173-177."""
+    W = np.random.random((d, k))
+    H = np.random.random((k, n))
+    return W, H
+
+
+def factorize(X, W, H, niter=1, compute_w=True, compute_h=True, compute_err=True,
+              early_stop=True, record=None):
+    """Driver loop.  pymf/nmf.py:141-202: per iteration W, then H, then error;
+    convergence is only checked for i > 1 and drops entry i of ferr.
+
+    W and H are float64 arrays updated in place.  Returns ferr (or None when
+    compute_err is False).  ``record(i, W, H, ferr_i)`` is called after every
+    iteration when given (parity harness).
+    """
+    ferr = np.zeros(niter) if compute_err else None        # :179-180
+    for i in range(niter):                                 # :182
+        if compute_w:
+            update_w(X, W, H)                              # :183-184
+        if compute_h:
+            update_h(X, W, H)                              # :186-187
+        if compute_err:
+            ferr[i] = frobenius_norm(X, W, H)              # :189-190
+        if record is not None:
+            record(i, W, H, ferr[i] if compute_err else None)
+        if early_stop and i > 1 and compute_err:           # :198-202
+            if converged(ferr, i, X.shape[1]):
+                ferr = ferr[:i]
+                break
+    return ferr
+
+
+# --------------------------------------------------------------------------
+# Synthetic inputs shared by tests, smoke() and bench.py.
+# The device generator in pymf_b200/csrc/pymfb.cu (k_gen_uniform) implements the
+# same integer hash so that any shard / tile regenerates bit-identically.
+# --------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def hash_uniform(seed, idx):
+    """U[0,1) float32 from a splitmix64-style hash of (seed, element index).
+
+    idx: uint64 array of global element indices.  Returns float32 with 24 random
+    mantissa bits: (h >> 40) * 2**-24.
+    """
+    with np.errstate(over="ignore"):
+        z = idx.astype(np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24))
+
+
+def gen_matrix(seed, rows, cols, ld=None, col0=0, ncols=None):
+    """rows x ncols block (columns col0..col0+ncols) of the synthetic rows x cols
+    matrix whose element (r, c) is hash_uniform(seed, r*ld + c); ld defaults to cols."""
+    ld = cols if ld is None else ld
+    ncols = cols - col0 if ncols is None else ncols
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    c = np.arange(col0, col0 + ncols, dtype=np.uint64)[None, :]
+    return hash_uniform(seed, r * np.uint64(ld) + c)

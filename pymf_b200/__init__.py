@@ -1,0 +1,11 @@
+"""pymf_b200 - B200-native implementation of pymf's NMF multiplicative-update path.
+
+``pymf_b200.NMF`` mirrors ``pymf.NMF`` (pymf/nmf.py); the compute runs in libpymfb.so
+(hand-written sm_100a CUDA behind the C ABI of include/pymfb.h).
+"""
+from .nmf import NMF  # noqa: F401
+from .engine import Engine  # noqa: F401
+from ._lib import PymfbError  # noqa: F401
+
+__all__ = ["NMF", "Engine", "PymfbError"]
+__version__ = "0.1.0"

@@ -1,0 +1,35 @@
+// common.cuh - shared definitions for libpymfb (NMF multiplicative updates on sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pymfb {
+
+constexpr float kEpsDenom = 1e-9f;   // pymf/nmf.py:124,130  (+ 10**-9 on the denominator)
+constexpr double kEpsConv = 1e-8;    // pymf/nmf.py:69,136   (NMF._EPS)
+
+// Device-resident loop state.  The stop decision of factorize() (pymf/nmf.py:198-202)
+// is taken on the device so that the host never synchronises inside the loop: once
+// `stop` is set every later kernel of the run returns immediately.
+struct DevState {
+    int stop;            // 1 after converged(i) fired
+    int n_exec;          // iterations executed when stop fired (i + 1)
+    unsigned ticket;     // last-block-done counter of the error reduction
+    unsigned ticket2;    // same, for ||X||^2
+    double xx;           // ||X||_F^2 over ALL ranks
+    double xx_local;     // this rank's share (all-reduced into xx)
+    double last_ferr;    // most recent error (pymfb_frobenius)
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
+    // splitmix64 finaliser; identical to oracle/nmf_oracle.py:hash_uniform
+    uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+    return (float)(uint32_t)(mix64(seed, idx) >> 40) * 5.9604644775390625e-08f;  // 2^-24
+}
+
+}  // namespace pymfb

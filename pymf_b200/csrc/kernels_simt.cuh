@@ -1,0 +1,452 @@
+// kernels_simt.cuh - fp32 CUDA-core kernels of the NMF multiplicative-update path.
+//
+// These are (a) the small replicated steps that stay on CUDA cores in every configuration
+// (W update, W^T W, the fp64 error combine, ||X||^2, casts, generators) and (b) the
+// any-shape streaming kernels (H update pass, X H^T pass) used when the tcgen05 path does
+// not apply (tiny / unaligned problems such as BASELINE cfg1, 1000x500 k=10).
+//
+// Reference arithmetic (pymf/nmf.py):
+//   update_h  :122-126   H <- H * (W^T X) / ((W^T W) H + 1e-9)
+//   update_w  :128-132   W <- W * (X H^T) / ((W H) H^T + 1e-9)   [= W (H H^T), re-associated]
+//   frobenius :100-114   sqrt(sum((X - W H)^2)) = sqrt(||X||^2 - 2<W, X H^T> + <W^T W, H H^T>)
+#pragma once
+#include "common.cuh"
+
+namespace pymfb {
+
+constexpr int SIMT_THREADS = 256;
+constexpr int TILE_N = 128;   // columns per CTA tile (4 per thread x 32 thread columns)
+constexpr int TILE_DK = 16;   // contraction rows staged per step
+
+// ---------------------------------------------------------------------------------------
+// acc[i][j] += sum_r L[r][lcol0 + ty*TK + i] * R[r][rcol0 + tx*4 + j]   for r in [r_begin, r_end)
+// L: rows x ldl (row-major), R: rows x ldr.  Columns of R >= r_ncols read as zero; rows are
+// bounded by r_end.  Column kb of L must be < ldl (L is padded to a multiple of KB).
+// 256 threads: tx = tid & 31 (4 R-columns each), ty = tid >> 5 (TK = KB/8 L-columns each).
+// ---------------------------------------------------------------------------------------
+template <int KB>
+__device__ __forceinline__ void tile_mac(float (&acc)[KB / 8][4],
+                                         const float* __restrict__ L, int64_t ldl, int lcol0,
+                                         const float* __restrict__ R, int64_t ldr, int64_t rcol0,
+                                         int64_t r_ncols, int64_t r_begin, int64_t r_end,
+                                         float (*Rs)[TILE_DK][TILE_N], float (*Ls)[TILE_DK][KB]) {
+    constexpr int TK = KB / 8;
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    constexpr int R_F4 = TILE_DK * TILE_N / 4 / SIMT_THREADS;   // float4 per thread for R (2)
+    constexpr int L_F4_TOTAL = TILE_DK * KB / 4;                // float4 in an L chunk
+    float4 rreg[R_F4];
+    float4 lreg;
+
+    auto load_chunk = [&](int64_t r0) {
+#pragma unroll
+        for (int t = 0; t < R_F4; ++t) {
+            int f = tid + t * SIMT_THREADS;
+            int row = f / (TILE_N / 4), c4 = f % (TILE_N / 4);
+            int64_t r = r0 + row, c = rcol0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < r_end && c < r_ncols) {
+                v = *reinterpret_cast<const float4*>(R + r * ldr + c);
+                if (c + 1 >= r_ncols) v.y = 0.f;
+                if (c + 2 >= r_ncols) v.z = 0.f;
+                if (c + 3 >= r_ncols) v.w = 0.f;
+            }
+            rreg[t] = v;
+        }
+        lreg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < L_F4_TOTAL) {
+            int row = tid / (KB / 4), c4 = tid % (KB / 4);
+            int64_t r = r0 + row;
+            if (r < r_end) lreg = *reinterpret_cast<const float4*>(L + r * ldl + lcol0 + c4 * 4);
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int t = 0; t < R_F4; ++t) {
+            int f = tid + t * SIMT_THREADS;
+            int row = f / (TILE_N / 4), c4 = f % (TILE_N / 4);
+            *reinterpret_cast<float4*>(&Rs[buf][row][c4 * 4]) = rreg[t];
+        }
+        if (tid < L_F4_TOTAL) {
+            int row = tid / (KB / 4), c4 = tid % (KB / 4);
+            *reinterpret_cast<float4*>(&Ls[buf][row][c4 * 4]) = lreg;
+        }
+    };
+
+    if (r_begin >= r_end) return;
+    load_chunk(r_begin);
+    store_chunk(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += TILE_DK) {
+        const bool has_next = r0 + TILE_DK < r_end;
+        if (has_next) load_chunk(r0 + TILE_DK);
+#pragma unroll
+        for (int r = 0; r < TILE_DK; ++r) {
+            float4 x = *reinterpret_cast<const float4*>(&Rs[buf][r][tx * 4]);
+            float w[TK];
+#pragma unroll
+            for (int i = 0; i < TK; ++i) w[i] = Ls[buf][r][ty * TK + i];
+#pragma unroll
+            for (int i = 0; i < TK; ++i) {
+                acc[i][0] = fmaf(w[i], x.x, acc[i][0]);
+                acc[i][1] = fmaf(w[i], x.y, acc[i][1]);
+                acc[i][2] = fmaf(w[i], x.z, acc[i][2]);
+                acc[i][3] = fmaf(w[i], x.w, acc[i][3]);
+            }
+        }
+        if (has_next) store_chunk(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// H update pass (pymf/nmf.py:122-126), any shape.
+//   grid.x = column tiles of 128, grid.y = k blocks of KB rows.
+//   C = W^T X  (contract over d),  D = G H (contract over kp),  Hn = H * C / (D + 1e-9)
+// Hc is read (all kp rows, for D), Hn is written (rows of this k block) -> ping-pong buffers.
+// ---------------------------------------------------------------------------------------
+template <int KB>
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
+                const float* __restrict__ W, const float* __restrict__ G,
+                const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
+                int64_t d, int64_t n_loc, int kp) {
+    if (st->stop) return;
+    constexpr int TK = KB / 8;
+    __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
+    __shared__ __align__(16) float Ls[2][TILE_DK][KB];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * TILE_N;
+    const int kb0 = blockIdx.y * KB;
+
+    float c[TK][4], dd[TK][4];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; dd[i][j] = 0.f; }
+
+    tile_mac<KB>(c, W, kp, kb0, X, ldx, col0, n_loc, 0, d, Rs, Ls);       // W^T X
+    tile_mac<KB>(dd, G, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);    // G H (G symmetric)
+
+    const int64_t col = col0 + tx * 4;
+    if (col >= n_loc) return;
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+        const int krow = kb0 + ty * TK + i;
+        const float4 h = *reinterpret_cast<const float4*>(Hc + (int64_t)krow * ldh + col);
+        float4 o;
+        o.x = (h.x * c[i][0]) / (dd[i][0] + kEpsDenom);
+        o.y = (col + 1 < n_loc) ? (h.y * c[i][1]) / (dd[i][1] + kEpsDenom) : 0.f;
+        o.z = (col + 2 < n_loc) ? (h.z * c[i][2]) / (dd[i][2] + kEpsDenom) : 0.f;
+        o.w = (col + 3 < n_loc) ? (h.w * c[i][3]) / (dd[i][3] + kEpsDenom) : 0.f;
+        *reinterpret_cast<float4*>(Hn + (int64_t)krow * ldh + col) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Out_partial[split][kb0 + ., col] = sum_{r in split} L[r][kb0 + .] * R[r][col]
+// Used for G = W^T W (L = R = W).  Deterministic: partials are summed in fixed order by
+// k_sum_partials, so every rank derives a bit-identical G from its bit-identical W.
+//   grid.x = column tiles (of kp), grid.y = k blocks, grid.z = row splits.
+// ---------------------------------------------------------------------------------------
+template <int KB>
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_ltr_partial_simt(const DevState* __restrict__ st, const float* __restrict__ L, int64_t ldl,
+                   const float* __restrict__ R, int64_t ldr, int64_t r_ncols, int64_t rows,
+                   int64_t rows_per_split, float* __restrict__ partial, int64_t out_ld,
+                   int64_t out_rows) {
+    if (st->stop) return;
+    constexpr int TK = KB / 8;
+    __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
+    __shared__ __align__(16) float Ls[2][TILE_DK][KB];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * TILE_N;
+    const int kb0 = blockIdx.y * KB;
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(rows, r_begin + rows_per_split);
+    float acc[TK][4];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    tile_mac<KB>(acc, L, ldl, kb0, R, ldr, col0, r_ncols, r_begin, r_end, Rs, Ls);
+    float* out = partial + (int64_t)blockIdx.z * out_rows * out_ld;
+    const int64_t col = col0 + tx * 4;
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+        const int krow = kb0 + ty * TK + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (col + j < r_ncols) out[(int64_t)krow * out_ld + col + j] = acc[i][j];
+    }
+}
+
+__global__ void k_sum_partials(const DevState* __restrict__ st, const float* __restrict__ partial,
+                               int nsplit, int64_t count, float* __restrict__ out) {
+    if (st->stop) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int p = 0; p < nsplit; ++p) s += partial[(int64_t)p * count + i];
+    out[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// P[row][kb0 + .] += sum_{c in column range} X[row][c] * H[kb0 + .][c]       (X H^T partials)
+// Also used for H H^T (X := H, rows := kp).  Accumulated with fp32 atomics into the packed
+// partial buffer that is all-reduced over ranks.
+//   grid.x = row blocks of 128, grid.y = column splits, grid.z = k blocks.
+// ---------------------------------------------------------------------------------------
+constexpr int XHT_CK = 32;
+template <int KB>
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t rows,
+           const float* __restrict__ H, int64_t ldh, int64_t n_loc, int64_t cols_per_split,
+           float* __restrict__ P, int64_t ldp) {
+    if (st->stop) return;
+    constexpr int TK = KB / 8;
+    __shared__ float Xs[128][XHT_CK + 1];
+    __shared__ __align__(16) float Hs[XHT_CK][KB];
+    const int tid = threadIdx.x;
+    const int tr = tid & 31, tk = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const int kb0 = blockIdx.z * KB;
+    const int64_t c_begin = (int64_t)blockIdx.y * cols_per_split;
+    const int64_t c_end = min(n_loc, c_begin + cols_per_split);
+
+    float acc[4][TK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TK; ++j) acc[i][j] = 0.f;
+
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += XHT_CK) {
+        // X chunk: 128 rows x 32 cols
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int f = tid + t * SIMT_THREADS;
+            int row = f >> 3, c4 = f & 7;
+            int64_t r = row0 + row, c = c0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows && c < c_end) {
+                v = *reinterpret_cast<const float4*>(X + r * ldx + c);
+                if (c + 1 >= c_end) v.y = 0.f;
+                if (c + 2 >= c_end) v.z = 0.f;
+                if (c + 3 >= c_end) v.w = 0.f;
+            }
+            Xs[row][c4 * 4 + 0] = v.x; Xs[row][c4 * 4 + 1] = v.y;
+            Xs[row][c4 * 4 + 2] = v.z; Xs[row][c4 * 4 + 3] = v.w;
+        }
+        // H chunk: KB rows x 32 cols, stored transposed [col][k]
+        for (int f = tid; f < KB * XHT_CK / 4; f += SIMT_THREADS) {
+            int krow = f >> 3, c4 = f & 7;
+            int64_t c = c0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < c_end) {
+                v = *reinterpret_cast<const float4*>(H + (int64_t)(kb0 + krow) * ldh + c);
+                if (c + 1 >= c_end) v.y = 0.f;
+                if (c + 2 >= c_end) v.z = 0.f;
+                if (c + 3 >= c_end) v.w = 0.f;
+            }
+            Hs[c4 * 4 + 0][krow] = v.x; Hs[c4 * 4 + 1][krow] = v.y;
+            Hs[c4 * 4 + 2][krow] = v.z; Hs[c4 * 4 + 3][krow] = v.w;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < XHT_CK; ++c) {
+            float x[4], h[TK];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = Xs[tr + 32 * i][c];
+#pragma unroll
+            for (int j = 0; j < TK; ++j) h[j] = Hs[c][tk * TK + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TK; ++j) acc[i][j] = fmaf(x[i], h[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + tr + 32 * i;
+        if (r < rows) {
+#pragma unroll
+            for (int j = 0; j < TK; ++j) atomicAdd(P + r * ldp + kb0 + tk * TK + j, acc[i][j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// W update (pymf/nmf.py:128-132), replicated on every rank, O(d k^2):
+//   Wn[i][j] = W[i][j] * A[i][j] / (sum_l W[i][l] B[l][j] + 1e-9)
+// 8 rows per CTA staged in shared memory; B (kp x kp) is read through L1/L2.
+// ---------------------------------------------------------------------------------------
+constexpr int UW_ROWS = 8;
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_update_w(const DevState* __restrict__ st, const float* __restrict__ W, const float* __restrict__ A,
+           const float* __restrict__ B, float* __restrict__ Wn, int64_t d, int kp) {
+    if (st->stop) return;
+    extern __shared__ float ws[];   // UW_ROWS x kp
+    const int64_t row0 = (int64_t)blockIdx.x * UW_ROWS;
+    const int nrows = (int)min((int64_t)UW_ROWS, d - row0);
+    for (int f = threadIdx.x; f < nrows * kp; f += blockDim.x) ws[f] = W[row0 * kp + f];
+    __syncthreads();
+    for (int f = threadIdx.x; f < nrows * kp; f += blockDim.x) {
+        const int r = f / kp, j = f % kp;
+        const float* wr = ws + r * kp;
+        float s = 0.f;
+        for (int l = 0; l < kp; ++l) s = fmaf(wr[l], B[(int64_t)l * kp + j], s);
+        const int64_t o = (row0 + r) * kp + j;
+        Wn[o] = (wr[j] * A[o]) / (s + kEpsDenom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Error (pymf/nmf.py:100-114 by the trace identity) + converged() (:134-139), fp64 combine.
+//   ferr = sqrt(max(0, ||X||^2 - 2 <W, A> + <G, B>)),  A = X H^T, B = H H^T, G = W^T W.
+// Block partial sums are combined in fixed order by the last block (deterministic, so all
+// ranks take the same stop decision).
+// ---------------------------------------------------------------------------------------
+constexpr int ERR_BLOCKS = 128;
+__global__ void __launch_bounds__(256)
+k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __restrict__ A,
+      int64_t n_wa, const float* __restrict__ G, const float* __restrict__ B, int64_t n_gb,
+      double* __restrict__ scratch /* 2*ERR_BLOCKS */, double* __restrict__ ferr, int iter,
+      double n_samples, int early_stop) {
+    if (st->stop) return;
+    __shared__ double s_wa[256], s_gb[256];
+    __shared__ bool is_last;
+    double wa = 0.0, gb = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_wa;
+         i += (int64_t)gridDim.x * blockDim.x)
+        wa += (double)W[i] * (double)A[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_gb;
+         i += (int64_t)gridDim.x * blockDim.x)
+        gb += (double)G[i] * (double)B[i];
+    s_wa[threadIdx.x] = wa; s_gb[threadIdx.x] = gb;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { s_wa[threadIdx.x] += s_wa[threadIdx.x + s]; s_gb[threadIdx.x] += s_gb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = s_wa[0];
+        scratch[ERR_BLOCKS + blockIdx.x] = s_gb[0];
+        __threadfence();
+        unsigned t = atomicAdd(&st->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double twa = 0.0, tgb = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            twa += ((volatile double*)scratch)[b];
+            tgb += ((volatile double*)scratch)[ERR_BLOCKS + b];
+        }
+        double e2 = st->xx - 2.0 * twa + tgb;
+        double e = sqrt(e2 > 0.0 ? e2 : 0.0);
+        st->last_ferr = e;
+        st->ticket = 0;
+        if (ferr) {
+            ferr[iter] = e;
+            if (early_stop && iter > 1) {
+                double derr = fabs(e - ferr[iter - 1]) / n_samples;
+                if (derr < kEpsConv) { st->stop = 1; st->n_exec = iter + 1; }
+            }
+        }
+    }
+}
+
+// ||X||_F^2 in fp64 (once per data set).
+constexpr int XX_BLOCKS = 1184;   // 8 x 148
+__global__ void __launch_bounds__(256)
+k_xx(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t d, int64_t n_loc,
+     double* __restrict__ scratch /* XX_BLOCKS */) {
+    __shared__ double s[256];
+    __shared__ bool is_last;
+    double acc = 0.0;
+    const int64_t n4 = (n_loc + 3) / 4;
+    const int64_t total = d * n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4, c = (i % n4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(X + r * ldx + c);
+        float p = v.x * v.x;
+        if (c + 1 < n_loc) p = fmaf(v.y, v.y, p);
+        if (c + 2 < n_loc) p = fmaf(v.z, v.z, p);
+        if (c + 3 < n_loc) p = fmaf(v.w, v.w, p);
+        acc += (double)p;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) s[threadIdx.x] += s[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = s[0];
+        __threadfence();
+        is_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) t += ((volatile double*)scratch)[b];
+        st->xx_local = t;
+        st->xx = t;          // overwritten by the all-reduce when there are several ranks
+        st->ticket2 = 0;
+    }
+}
+
+// --- small utilities ---------------------------------------------------------------------
+__global__ void k_zero(const DevState* __restrict__ st, float* __restrict__ p, int64_t count) {
+    if (st->stop) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) p[i] = 0.f;
+}
+
+// dst (rows x ldd, fp32) <- src (rows x cols, T contiguous with leading dimension lds)
+template <typename T>
+__global__ void k_cast_in(const T* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                          int64_t rows, int64_t cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < rows * cols; i += stride) {
+        const int64_t r = i / cols, c = i % cols;
+        dst[r * ldd + c] = (float)src[r * lds + c];
+    }
+}
+template <typename T>
+__global__ void k_cast_out(const float* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd,
+                           int64_t rows, int64_t cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < rows * cols; i += stride) {
+        const int64_t r = i / cols, c = i % cols;
+        dst[r * ldd + c] = (T)src[r * lds + c];
+    }
+}
+
+// dst[r][c] = U[0,1) hash(seed, r * gen_ld + gen_col0 + c)  for r < rows, c < cols (pad stays 0)
+__global__ void k_gen_uniform(float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
+                              uint64_t seed, int64_t gen_ld, int64_t gen_col0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < rows * cols; i += stride) {
+        const int64_t r = i / cols, c = i % cols;
+        dst[r * ldd + c] = hash_uniform(seed, (uint64_t)(r * gen_ld + gen_col0 + c));
+    }
+}
+
+__global__ void k_fill(float* __restrict__ p, int64_t count, float v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) p[i] = v;
+}
+
+}  // namespace pymfb

@@ -1,0 +1,742 @@
+// pymfb.cu - context, scheduling of the per-iteration kernels, and the C ABI (include/pymfb.h).
+//
+// Path served: pymf.NMF.factorize -> update_w / update_h / frobenius_norm / converged
+// (pymf/nmf.py:100-202).  State kept on the device between iterations:
+//   W (d x kp), H (kp x ldh) ping-pong pairs; P = [X H^T | H H^T] local partials;
+//   AB = the same after the all-reduce over ranks; G = W^T W; ||X||^2.
+// One iteration (W, then H, then error - the reference's order, :183-190):
+//   W  <- W * A / (W B + 1e-9)                 k_update_w           (replicated, O(d k^2))
+//   G  <- W^T W                                k_ltr_partial + sum  (replicated, O(d k^2))
+//   H  <- H * (W^T X) / (G H + 1e-9)           H-update pass        (streams X)
+//   P  <- [X H^T | H H^T]                      X H^T pass           (streams X)
+//   AB <- allreduce(P)                         NCCL (world > 1)
+//   ferr_i = sqrt(xx - 2<W,A> + <G,B>)         k_err (fp64), device-side stop flag
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/pymfb.h"
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+using namespace pymfb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CK(call)                      \
+    do {                              \
+        int r_ = (call);              \
+        if (r_ != 0) return r_;       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (so that the library loads on a box without NCCL / without a GPU)
+// ------------------------------------------------------------------------------------------
+struct Uid128 { char b[128]; };   // ncclUniqueId (passed by value)
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Uid128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static const int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (h) break; }
+    if (!h) for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Uid128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail("libnccl is missing required symbols");
+    g_nccl.lib = h;
+    return 0;
+}
+#define NC(call)                                                                         \
+    do {                                                                                 \
+        int r_ = (call);                                                                 \
+        if (r_ != 0)                                                                     \
+            return fail("%s:%d %s -> nccl error %d (%s)", __FILE__, __LINE__, #call, r_, \
+                        g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?");        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct pymfb_ctx {
+    int device = 0;
+    int64_t d = 0, n_loc = 0, n_glob = 0, col0 = 0;
+    int k = 0, kp = 0, kb = 0;     // kp: padded k; kb: SIMT k block
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+
+    const float* X = nullptr;      // d x ldx
+    float* X_own = nullptr;
+    int64_t ldx = 0;
+
+    float* W[2] = {nullptr, nullptr};   // d x kp
+    float* H[2] = {nullptr, nullptr};   // kp x ldh
+    int wcur = 0, hcur = 0;
+    int64_t ldh = 0;
+    bool w_set = false, h_set = false;
+
+    float* P = nullptr;            // local partials [A (d x kp) | B (kp x kp)]
+    float* AB = nullptr;           // reduced (== P when world == 1)
+    int64_t ab_count = 0;
+    float* G = nullptr;            // kp x kp
+    float* Gpart = nullptr;        // g_splits x kp x kp
+    int g_splits = 1;
+    int64_t g_rows_per_split = 0;
+    double* red_scratch = nullptr; // fp64 block partials (k_err, k_xx)
+    DevState* st = nullptr;
+    double* ferr_dev = nullptr;
+    int ferr_cap = 0;
+    float* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+
+    bool ab_valid = false;         // AB matches the current H (and X)
+    bool g_valid = false;          // G matches the current W
+    bool xx_valid = false;
+
+    int path_opt = PYMFB_PATH_AUTO;
+    int path = PYMFB_PATH_SIMT;
+    TcPlan tc;                     // tensor-core plan (kernels_tc.cuh)
+
+    void* comm = nullptr;
+    int world = 1, rank = 0;
+
+    int64_t launches = 0;
+
+    // per-kernel timing (CUDA events on the launch stream)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int grid_for(int64_t count, int block, int cap) {
+    int64_t g = (count + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+static int timing_begin(pymfb_ctx* c, int which, cudaEvent_t* e0, cudaEvent_t* e1) {
+    *e0 = *e1 = nullptr;
+    if (!c->timing || c->ev[which].size() >= 4096) return 0;
+    CU(cudaEventCreate(e0));
+    CU(cudaEventCreate(e1));
+    CU(cudaEventRecord(*e0, c->stream));
+    return 0;
+}
+static int timing_end(pymfb_ctx* c, int which, cudaEvent_t e0, cudaEvent_t e1) {
+    if (!e0) return 0;
+    CU(cudaEventRecord(e1, c->stream));
+    c->ev[which].push_back({e0, e1});
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel scheduling helpers
+// ------------------------------------------------------------------------------------------
+static int resolve_path(pymfb_ctx* c) {
+    std::string why;
+    bool ok = tc_supported(c->d, c->n_loc, c->kp, c->ldx, c->X, &why);
+    if (c->path_opt == PYMFB_PATH_SIMT) { c->path = PYMFB_PATH_SIMT; return 0; }
+    if (c->path_opt == PYMFB_PATH_TC) {
+        if (!ok) return fail("tcgen05 path not available for this shape: %s", why.c_str());
+        c->path = PYMFB_PATH_TC;
+        return 0;
+    }
+    c->path = ok ? PYMFB_PATH_TC : PYMFB_PATH_SIMT;
+    return 0;
+}
+
+// G = W^T W (deterministic two-stage sum)
+static int launch_gram_w(pymfb_ctx* c) {
+    const float* W = c->W[c->wcur];
+    dim3 grid((unsigned)((c->kp + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb), (unsigned)c->g_splits);
+    if (c->kb == 16)
+        k_ltr_partial_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, W, c->kp, W, c->kp, c->kp, c->d,
+                                                                     c->g_rows_per_split, c->Gpart, c->kp, c->kp);
+    else
+        k_ltr_partial_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, W, c->kp, W, c->kp, c->kp, c->d,
+                                                                     c->g_rows_per_split, c->Gpart, c->kp, c->kp);
+    const int64_t cnt = (int64_t)c->kp * c->kp;
+    k_sum_partials<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->st, c->Gpart, c->g_splits, cnt, c->G);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    if (c->path == PYMFB_PATH_TC) CK(tc_after_gram(c->tc, c->st, c->W[c->wcur], c->G, c->stream, &c->launches));
+    c->g_valid = true;
+    return 0;
+}
+
+static int launch_update_w(pymfb_ctx* c) {
+    const float* A = c->AB;
+    const float* B = c->AB + c->d * c->kp;
+    unsigned grid = (unsigned)((c->d + UW_ROWS - 1) / UW_ROWS);
+    size_t smem = (size_t)UW_ROWS * c->kp * sizeof(float);
+    k_update_w<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, c->W[c->wcur], A, B, c->W[c->wcur ^ 1], c->d, c->kp);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->wcur ^= 1;
+    c->g_valid = false;
+    return 0;
+}
+
+// H update pass: H[hcur] -> H[hcur^1]
+static int launch_h_update(pymfb_ctx* c) {
+    cudaEvent_t e0, e1;
+    CK(timing_begin(c, 0, &e0, &e1));
+    if (c->path == PYMFB_PATH_TC) {
+        CK(tc_h_update(c->tc, c->st, c->X, c->ldx, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches));
+    } else {
+        dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
+        if (c->kb == 16)
+            k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
+                                                                      c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
+                                                                      c->d, c->n_loc, c->kp);
+        else
+            k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
+                                                                      c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
+                                                                      c->d, c->n_loc, c->kp);
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
+    CK(timing_end(c, 0, e0, e1));
+    c->hcur ^= 1;
+    c->ab_valid = false;
+    return 0;
+}
+
+static void xht_splits(pymfb_ctx* c, int64_t rows, int64_t* cols_per_split, unsigned* nsplit) {
+    const int64_t rowblocks = (rows + 127) / 128, kblocks = c->kp / c->kb;
+    const int64_t chunks = (c->n_loc + XHT_CK - 1) / XHT_CK;
+    int64_t want = std::max<int64_t>(1, (4LL * c->sm_count) / (rowblocks * kblocks));
+    want = std::min(want, chunks);
+    int64_t chunks_per = (chunks + want - 1) / want;
+    *cols_per_split = chunks_per * XHT_CK;
+    *nsplit = (unsigned)((chunks + chunks_per - 1) / chunks_per);
+}
+
+// P = [X H^T | H H^T] for the current H, then AB = allreduce(P)
+static int launch_xht(pymfb_ctx* c) {
+    const float* Hc = c->H[c->hcur];
+    k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
+    c->launches += 1;
+    cudaEvent_t e0, e1;
+    CK(timing_begin(c, 1, &e0, &e1));
+    if (c->path == PYMFB_PATH_TC) {
+        CK(tc_xht(c->tc, c->st, c->X, c->ldx, Hc, c->P, c->stream, &c->launches));
+    } else {
+        int64_t cps; unsigned ns;
+        xht_splits(c, c->d, &cps, &ns);
+        dim3 grid((unsigned)((c->d + 127) / 128), ns, (unsigned)(c->kp / c->kb));
+        if (c->kb == 16)
+            k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp);
+        else
+            k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp);
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
+    CK(timing_end(c, 1, e0, e1));
+    {   // B = H H^T  (X := H)
+        int64_t cps; unsigned ns;
+        xht_splits(c, c->kp, &cps, &ns);
+        dim3 grid((unsigned)((c->kp + 127) / 128), ns, (unsigned)(c->kp / c->kb));
+        float* PB = c->P + c->d * c->kp;
+        if (c->kb == 16)
+            k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, Hc, c->ldh, c->kp, Hc, c->ldh, c->n_loc, cps, PB, c->kp);
+        else
+            k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, Hc, c->ldh, c->kp, Hc, c->ldh, c->n_loc, cps, PB, c->kp);
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (c->world > 1)
+        NC(g_nccl.AllReduce(c->P, c->AB, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
+    c->ab_valid = true;
+    return 0;
+}
+
+static int launch_xx(pymfb_ctx* c) {
+    k_xx<<<XX_BLOCKS, 256, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, c->n_loc, c->red_scratch);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    if (c->world > 1)
+        NC(g_nccl.AllReduce(&c->st->xx_local, &c->st->xx, 1, kNcclFloat64, kNcclSum, c->comm, c->stream));
+    c->xx_valid = true;
+    return 0;
+}
+
+static int launch_err(pymfb_ctx* c, int iter, bool store, bool early_stop) {
+    const float* A = c->AB;
+    const float* B = c->AB + c->d * c->kp;
+    k_err<<<ERR_BLOCKS, 256, 0, c->stream>>>(c->st, c->W[c->wcur], A, c->d * c->kp, c->G, B, (int64_t)c->kp * c->kp,
+                                             c->red_scratch, store ? c->ferr_dev : nullptr, iter,
+                                             (double)c->n_glob, early_stop ? 1 : 0);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int check_ready(pymfb_ctx* c) {
+    if (!c) return fail("null context");
+    if (!c->X) return fail("no data bound: call pymfb_bind_x / pymfb_upload_x / pymfb_gen_x first");
+    if (!c->w_set || !c->h_set) return fail("W and H must be set (pymfb_set_w/h or pymfb_gen_w/h) before running");
+    return 0;
+}
+
+static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
+    CK(check_ready(c));
+    CU(cudaSetDevice(c->device));
+    const bool do_w = flags & PYMFB_COMPUTE_W, do_h = flags & PYMFB_COMPUTE_H, do_e = flags & PYMFB_COMPUTE_ERR;
+    const bool early = (flags & PYMFB_EARLY_STOP) && do_e;
+    if (do_e && !c->xx_valid) CK(launch_xx(c));
+    for (int i = 0; i < niter; ++i) {
+        if (do_w) {
+            if (!c->ab_valid) CK(launch_xht(c));      // bootstrap: A, B of the current H
+            CK(launch_update_w(c));
+        }
+        if (do_h) {
+            if (!c->g_valid) CK(launch_gram_w(c));
+            CK(launch_h_update(c));
+            // A, B of the new H feed the next W update and this iteration's error
+            if (do_e || (do_w && i + 1 < niter)) CK(launch_xht(c));
+        }
+        if (do_e) {
+            if (!c->g_valid) CK(launch_gram_w(c));
+            if (!c->ab_valid) CK(launch_xht(c));
+            CK(launch_err(c, i, true, early));
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int pymfb_version(void) { return 1000; }
+const char* pymfb_last_error(void) { return g_err; }
+
+int pymfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_t n_global, int64_t col0, int k) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (d <= 0 || n_local <= 0 || k <= 0 || n_global < n_local) return fail("bad shape d=%lld n_local=%lld n_global=%lld k=%d", (long long)d, (long long)n_local, (long long)n_global, k);
+    int ndev = pymfb_device_count();
+    if (ndev <= 0) return fail("no CUDA device available: libpymfb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; libpymfb is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    pymfb_ctx* c = new pymfb_ctx();
+    c->device = device; c->d = d; c->n_loc = n_local; c->n_glob = n_global; c->col0 = col0; c->k = k;
+    c->kp = (int)(k <= 16 ? 16 : round_up(k, 32));
+    c->kb = std::min(c->kp, 32);
+    c->sm_count = prop.multiProcessorCount;
+    c->ldh = round_up(n_local, 32);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t wbytes = (size_t)d * c->kp * sizeof(float), hbytes = (size_t)c->kp * c->ldh * sizeof(float);
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&c->W[i], wbytes)); CU(cudaMemsetAsync(c->W[i], 0, wbytes, c->stream));
+        CU(cudaMalloc(&c->H[i], hbytes)); CU(cudaMemsetAsync(c->H[i], 0, hbytes, c->stream));
+    }
+    c->ab_count = d * c->kp + (int64_t)c->kp * c->kp;
+    CU(cudaMalloc(&c->P, c->ab_count * sizeof(float)));
+    CU(cudaMemsetAsync(c->P, 0, c->ab_count * sizeof(float), c->stream));
+    c->AB = c->P;   // separate buffer is allocated by pymfb_comm_init
+    CU(cudaMalloc(&c->G, (size_t)c->kp * c->kp * sizeof(float)));
+    // row splits of the W^T W reduction: enough CTAs to cover the SMs, >= 64 rows each
+    {
+        int64_t tiles = ((c->kp + TILE_N - 1) / TILE_N) * (c->kp / c->kb);
+        int64_t want = std::max<int64_t>(1, (2LL * c->sm_count) / tiles);
+        int64_t max_by_rows = std::max<int64_t>(1, d / 64);
+        c->g_splits = (int)std::min(want, max_by_rows);
+        c->g_rows_per_split = round_up((d + c->g_splits - 1) / c->g_splits, TILE_DK);
+        c->g_splits = (int)((d + c->g_rows_per_split - 1) / c->g_rows_per_split);
+    }
+    CU(cudaMalloc(&c->Gpart, (size_t)c->g_splits * c->kp * c->kp * sizeof(float)));
+    CU(cudaMalloc(&c->red_scratch, sizeof(double) * std::max(2 * ERR_BLOCKS, XX_BLOCKS)));
+    CU(cudaMalloc(&c->st, sizeof(DevState)));
+    CU(cudaMemsetAsync(c->st, 0, sizeof(DevState), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+int pymfb_destroy(pymfb_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    tc_release(c->tc);
+    for (int w = 0; w < 2; ++w)
+        for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (c->AB != c->P) cudaFree(c->AB);
+    cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
+    cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->W[i]); cudaFree(c->H[i]); }
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
+    if (!c) return fail("null context");
+    if (option == PYMFB_OPT_PATH) {
+        if (value < 0 || value > 2) return fail("bad path option %lld", (long long)value);
+        c->path_opt = (int)value;
+        if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC) CK(tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh)); c->g_valid = false; }
+        return 0;
+    }
+    return fail("unknown option %d", option);
+}
+
+int pymfb_comm_unique_id(void* out128) {
+    CK(nccl_load());
+    NC(g_nccl.GetUniqueId(out128));
+    return 0;
+}
+
+int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
+    if (!c) return fail("null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad world/rank %d/%d", world, rank);
+    if (world == 1) return 0;
+    CK(nccl_load());
+    CU(cudaSetDevice(c->device));
+    Uid128 uid;
+    memcpy(&uid, uid128, sizeof(uid));
+    NC(g_nccl.CommInitRank(&c->comm, world, uid, rank));
+    c->world = world; c->rank = rank;
+    CU(cudaMalloc(&c->AB, c->ab_count * sizeof(float)));
+    CU(cudaMemset(c->AB, 0, c->ab_count * sizeof(float)));
+    c->ab_valid = false; c->xx_valid = false;
+    return 0;
+}
+
+static int data_changed(pymfb_ctx* c) {
+    c->ab_valid = false; c->xx_valid = false;
+    CK(resolve_path(c));
+    if (c->path == PYMFB_PATH_TC) CK(tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh));
+    c->g_valid = false;
+    return 0;
+}
+
+static int ensure_own_x(pymfb_ctx* c) {
+    if (!c->X_own) {
+        c->ldx = round_up(c->n_loc, 32);
+        CU(cudaMalloc(&c->X_own, (size_t)c->d * c->ldx * sizeof(float)));
+        CU(cudaMemsetAsync(c->X_own, 0, (size_t)c->d * c->ldx * sizeof(float), c->stream));
+    }
+    c->ldx = round_up(c->n_loc, 32);
+    c->X = c->X_own;
+    return 0;
+}
+
+int pymfb_bind_x(pymfb_ctx* c, const float* x_dev, int64_t ld) {
+    if (!c) return fail("null context");
+    if (!x_dev) return fail("x_dev is null");
+    if (ld < c->n_loc || (ld % 4) != 0) return fail("leading dimension %lld must be >= n_local and a multiple of 4", (long long)ld);
+    if (((uintptr_t)x_dev & 15) != 0) return fail("x_dev must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    c->X = x_dev; c->ldx = ld;
+    return data_changed(c);
+}
+
+int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
+    if (!c) return fail("null context");
+    if (!x_host) return fail("x_host is null");
+    if (ld < c->n_loc) return fail("leading dimension too small");
+    CU(cudaSetDevice(c->device));
+    CK(ensure_own_x(c));
+    if (dtype == PYMFB_F32) {
+        CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), x_host, ld * sizeof(float),
+                             c->n_loc * sizeof(float), c->d, cudaMemcpyHostToDevice, c->stream));
+    } else if (dtype == PYMFB_F64) {
+        // chunked: rows of fp64 -> device staging -> cast kernel
+        const int64_t max_chunk_bytes = 256LL << 20;
+        int64_t rows_per = std::max<int64_t>(1, max_chunk_bytes / (int64_t)(c->n_loc * sizeof(double)));
+        rows_per = std::min(rows_per, c->d);
+        double* stage = nullptr;
+        CU(cudaMalloc(&stage, (size_t)rows_per * c->n_loc * sizeof(double)));
+        for (int64_t r0 = 0; r0 < c->d; r0 += rows_per) {
+            int64_t nr = std::min(rows_per, c->d - r0);
+            CU(cudaMemcpy2DAsync(stage, c->n_loc * sizeof(double), (const double*)x_host + r0 * ld, ld * sizeof(double),
+                                 c->n_loc * sizeof(double), nr, cudaMemcpyHostToDevice, c->stream));
+            k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
+                stage, c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
+            c->launches += 1;
+            CU(cudaGetLastError());
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(stage));
+    } else {
+        return fail("bad dtype %d", dtype);
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return data_changed(c);
+}
+
+int pymfb_gen_x(pymfb_ctx* c, uint64_t seed) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CK(ensure_own_x(c));
+    k_gen_uniform<<<grid_for(c->d * c->n_loc, 256, 32 * c->sm_count), 256, 0, c->stream>>>(
+        c->X_own, c->ldx, c->d, c->n_loc, seed, c->n_glob, c->col0);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return data_changed(c);
+}
+
+// host (rows x cols, dense, dtype) -> device fp32 (rows x ldd), padding zeroed
+static int set_factor(pymfb_ctx* c, float* dst, int64_t ldd, int64_t rows_alloc, int64_t rows, int64_t cols,
+                      const void* host, int dtype) {
+    if (!host) return fail("host pointer is null");
+    if (dtype != PYMFB_F32 && dtype != PYMFB_F64) return fail("bad dtype %d", dtype);
+    CU(cudaSetDevice(c->device));
+    const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, (size_t)rows * cols * esz));
+    CU(cudaMemcpyAsync(stage, host, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(dst, 0, (size_t)rows_alloc * ldd * sizeof(float), c->stream));
+    const int g = grid_for(rows * cols, 256, 16 * c->sm_count);
+    if (dtype == PYMFB_F32) k_cast_in<float><<<g, 256, 0, c->stream>>>((const float*)stage, cols, dst, ldd, rows, cols);
+    else k_cast_in<double><<<g, 256, 0, c->stream>>>((const double*)stage, cols, dst, ldd, rows, cols);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(stage));
+    return 0;
+}
+static int get_factor(pymfb_ctx* c, const float* src, int64_t lds, int64_t rows, int64_t cols, void* host, int dtype) {
+    if (!host) return fail("host pointer is null");
+    if (dtype != PYMFB_F32 && dtype != PYMFB_F64) return fail("bad dtype %d", dtype);
+    CU(cudaSetDevice(c->device));
+    const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, (size_t)rows * cols * esz));
+    const int g = grid_for(rows * cols, 256, 16 * c->sm_count);
+    if (dtype == PYMFB_F32) k_cast_out<float><<<g, 256, 0, c->stream>>>(src, lds, (float*)stage, cols, rows, cols);
+    else k_cast_out<double><<<g, 256, 0, c->stream>>>(src, lds, (double*)stage, cols, rows, cols);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, stage, (size_t)rows * cols * esz, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(stage));
+    return 0;
+}
+
+int pymfb_set_w(pymfb_ctx* c, const void* w_host, int dtype) {
+    if (!c) return fail("null context");
+    CK(set_factor(c, c->W[c->wcur], c->kp, c->d, c->d, c->k, w_host, dtype));
+    c->w_set = true; c->g_valid = false;
+    return 0;
+}
+int pymfb_set_h(pymfb_ctx* c, const void* h_host, int dtype) {
+    if (!c) return fail("null context");
+    CK(set_factor(c, c->H[c->hcur], c->ldh, c->kp, c->k, c->n_loc, h_host, dtype));
+    c->h_set = true; c->ab_valid = false;
+    return 0;
+}
+int pymfb_get_w(pymfb_ctx* c, void* w_host, int dtype) {
+    if (!c) return fail("null context");
+    if (!c->w_set) return fail("W is not set");
+    return get_factor(c, c->W[c->wcur], c->kp, c->d, c->k, w_host, dtype);
+}
+int pymfb_get_h(pymfb_ctx* c, void* h_host, int dtype) {
+    if (!c) return fail("null context");
+    if (!c->h_set) return fail("H is not set");
+    return get_factor(c, c->H[c->hcur], c->ldh, c->k, c->n_loc, h_host, dtype);
+}
+int pymfb_gen_w(pymfb_ctx* c, uint64_t seed) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->W[c->wcur], 0, (size_t)c->d * c->kp * sizeof(float), c->stream));
+    k_gen_uniform<<<grid_for(c->d * c->k, 256, 16 * c->sm_count), 256, 0, c->stream>>>(c->W[c->wcur], c->kp, c->d, c->k, seed, c->k, 0);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->w_set = true; c->g_valid = false;
+    return 0;
+}
+int pymfb_gen_h(pymfb_ctx* c, uint64_t seed) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->H[c->hcur], 0, (size_t)c->kp * c->ldh * sizeof(float), c->stream));
+    k_gen_uniform<<<grid_for((int64_t)c->k * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(c->H[c->hcur], c->ldh, c->k, c->n_loc, seed, c->n_glob, c->col0);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    c->h_set = true; c->ab_valid = false;
+    return 0;
+}
+
+int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n_iter_done, int* n_ferr) {
+    CK(check_ready(c));
+    if (niter < 0) return fail("niter < 0");
+    const bool do_e = flags & PYMFB_COMPUTE_ERR;
+    if (do_e && niter > 0 && !ferr_host) return fail("ferr_host is null but PYMFB_COMPUTE_ERR is set");
+    CU(cudaSetDevice(c->device));
+    if (do_e && niter > c->ferr_cap) {
+        if (c->ferr_dev) CU(cudaFree(c->ferr_dev));
+        c->ferr_cap = std::max(niter, 1024);
+        CU(cudaMalloc(&c->ferr_dev, sizeof(double) * c->ferr_cap));
+    }
+    const int w0 = c->wcur, h0 = c->hcur;
+    CK(enqueue_iterations(c, niter, flags));
+    DevState hs;
+    CU(cudaMemcpyAsync(&hs, c->st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int done = niter, nf = do_e ? niter : 0;
+    if (hs.stop) {
+        // converged(i) fired at i = n_exec - 1: W/H keep iteration i's update, entry i of ferr
+        // is dropped (pymf/nmf.py:199-202).  Kernels after the stop were no-ops, so the live
+        // ping-pong buffers are the ones after n_exec swaps.
+        done = hs.n_exec;
+        nf = hs.n_exec - 1;
+        if (flags & PYMFB_COMPUTE_W) c->wcur = w0 ^ (done & 1);
+        if (flags & PYMFB_COMPUTE_H) c->hcur = h0 ^ (done & 1);
+        CU(cudaMemsetAsync(&c->st->stop, 0, sizeof(int), c->stream));
+        c->g_valid = false;   // recomputed lazily for the surviving W
+        c->ab_valid = false;
+    }
+    if (do_e && nf > 0) CU(cudaMemcpyAsync(ferr_host, c->ferr_dev, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_iter_done) *n_iter_done = done;
+    if (n_ferr) *n_ferr = nf;
+    return 0;
+}
+
+int pymfb_frobenius(pymfb_ctx* c, double* out) {
+    CK(check_ready(c));
+    if (!out) return fail("out is null");
+    CU(cudaSetDevice(c->device));
+    if (!c->xx_valid) CK(launch_xx(c));
+    if (!c->g_valid) CK(launch_gram_w(c));
+    if (!c->ab_valid) CK(launch_xht(c));
+    CK(launch_err(c, 0, false, false));
+    DevState hs;
+    CU(cudaMemcpyAsync(&hs, c->st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = hs.last_ferr;
+    return 0;
+}
+
+int pymfb_enqueue(pymfb_ctx* c, int niter, unsigned flags) {
+    if (flags & PYMFB_EARLY_STOP) return fail("pymfb_enqueue does not support PYMFB_EARLY_STOP (use pymfb_run)");
+    if ((flags & PYMFB_COMPUTE_ERR) && niter > c->ferr_cap) {
+        CU(cudaSetDevice(c->device));
+        if (c->ferr_dev) CU(cudaFree(c->ferr_dev));
+        c->ferr_cap = std::max(niter, 1024);
+        CU(cudaMalloc(&c->ferr_dev, sizeof(double) * c->ferr_cap));
+    }
+    return enqueue_iterations(c, niter, flags);
+}
+int pymfb_sync(pymfb_ctx* c) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void* pymfb_stream(pymfb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pymfb_event_create(void** ev) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    *ev = (void*)e;
+    return 0;
+}
+int pymfb_event_record(pymfb_ctx* c, void* ev) {
+    if (!c) return fail("null context");
+    CU(cudaEventRecord((cudaEvent_t)ev, c->stream));
+    return 0;
+}
+int pymfb_event_elapsed_ms(void* a, void* b, float* ms) {
+    CU(cudaEventSynchronize((cudaEvent_t)b));
+    CU(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return 0;
+}
+int pymfb_event_destroy(void* ev) { CU(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
+
+int pymfb_kernel_timing(pymfb_ctx* c, int enable) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < 2; ++w) {
+        for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        c->ev[w].clear();
+    }
+    c->timing = enable != 0;
+    return 0;
+}
+int pymfb_kernel_timing_read(pymfb_ctx* c, int which, double* avg_ms, int64_t* launches) {
+    if (!c) return fail("null context");
+    if (which < 0 || which > 1) return fail("which must be 0 or 1");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (auto& p : c->ev[which]) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p.first, p.second));
+        tot += ms;
+    }
+    const int64_t n = (int64_t)c->ev[which].size();
+    if (avg_ms) *avg_ms = n ? tot / n : 0.0;
+    if (launches) *launches = n;
+    return 0;
+}
+
+int64_t pymfb_launch_count(pymfb_ctx* c) { return c ? c->launches : 0; }
+int pymfb_active_path(pymfb_ctx* c) { return c ? c->path : 0; }
+
+int pymfb_flush_l2(pymfb_ctx* c) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    if (!c->flush_buf) {
+        c->flush_bytes = 256u << 20;   // > 126 MB L2
+        CU(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    k_fill<<<8 * c->sm_count, 256, 0, c->stream>>>(c->flush_buf, (int64_t)(c->flush_bytes / sizeof(float)), 1.0f);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""Engine: one libpymfb context (= one GPU, one column shard of X and H).
+
+Thin object wrapper over the C ABI; all arithmetic happens in the CUDA library.  The
+reference has no counterpart below the NMF class - this is the layer pymf.NMF's hooks
+(update_w / update_h / frobenius_norm, pymf/nmf.py:100-132) are rebuilt on.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _dtype_code(a):
+    if a.dtype == np.float32:
+        return _lib.F32
+    if a.dtype == np.float64:
+        return _lib.F64
+    raise TypeError("expected float32/float64, got %s" % a.dtype)
+
+
+class Engine(object):
+    def __init__(self, d, n_local, k, device=0, n_global=None, col0=0, path=None):
+        self._lib = _lib.load()
+        self.d, self.n_local, self.k = int(d), int(n_local), int(k)
+        self.n_global = int(n_local if n_global is None else n_global)
+        self.col0 = int(col0)
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        self._keepalive = None
+        _lib.check(self._lib.pymfb_create(C.byref(self._ctx), self.device, self.d, self.n_local,
+                                          self.n_global, self.col0, self.k))
+        if path is not None:
+            self.set_path(path)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.pymfb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- options / comm -----------------------------------------------------------------
+    def set_path(self, path):
+        code = {"auto": _lib.PATH_AUTO, "simt": _lib.PATH_SIMT, "tc": _lib.PATH_TC}.get(path, path)
+        _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_PATH, int(code)))
+
+    @property
+    def active_path(self):
+        return {_lib.PATH_SIMT: "simt", _lib.PATH_TC: "tc"}.get(self._lib.pymfb_active_path(self._ctx), "?")
+
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().pymfb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid, world, rank):
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _lib.check(self._lib.pymfb_comm_init(self._ctx, buf, int(world), int(rank)))
+
+    # -- data -----------------------------------------------------------------------------
+    def upload_x(self, x):
+        """x: host array (d x n_local), float32 or float64, last axis contiguous."""
+        x = np.asarray(x)
+        if x.shape != (self.d, self.n_local):
+            raise ValueError("data shape %r != (%d, %d)" % (x.shape, self.d, self.n_local))
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        if x.strides[1] != x.itemsize or x.strides[0] % x.itemsize or x.strides[0] < x.shape[1] * x.itemsize:
+            x = np.ascontiguousarray(x)
+        ld = x.strides[0] // x.itemsize
+        _lib.check(self._lib.pymfb_upload_x(self._ctx, x.ctypes.data_as(C.c_void_p), _dtype_code(x), ld))
+
+    def bind_x_device(self, ptr, ld, keepalive=None):
+        """Borrow a device pointer (fp32 row-major d x n_local, leading dimension ld)."""
+        self._keepalive = keepalive
+        _lib.check(self._lib.pymfb_bind_x(self._ctx, C.c_void_p(int(ptr)), int(ld)))
+
+    def gen_x(self, seed):
+        _lib.check(self._lib.pymfb_gen_x(self._ctx, int(seed)))
+
+    def gen_w(self, seed):
+        _lib.check(self._lib.pymfb_gen_w(self._ctx, int(seed)))
+
+    def gen_h(self, seed):
+        _lib.check(self._lib.pymfb_gen_h(self._ctx, int(seed)))
+
+    def _host_in(self, a, shape, what):
+        a = np.ascontiguousarray(a)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        if a.shape != shape:
+            raise ValueError("%s shape %r != %r" % (what, a.shape, shape))
+        return a
+
+    def set_w(self, w):
+        w = self._host_in(w, (self.d, self.k), "W")
+        _lib.check(self._lib.pymfb_set_w(self._ctx, w.ctypes.data_as(C.c_void_p), _dtype_code(w)))
+
+    def set_h(self, h):
+        h = self._host_in(h, (self.k, self.n_local), "H")
+        _lib.check(self._lib.pymfb_set_h(self._ctx, h.ctypes.data_as(C.c_void_p), _dtype_code(h)))
+
+    def get_w(self, dtype=np.float64):
+        out = np.empty((self.d, self.k), dtype=dtype)
+        _lib.check(self._lib.pymfb_get_w(self._ctx, out.ctypes.data_as(C.c_void_p), _dtype_code(out)))
+        return out
+
+    def get_h(self, dtype=np.float64):
+        out = np.empty((self.k, self.n_local), dtype=dtype)
+        _lib.check(self._lib.pymfb_get_h(self._ctx, out.ctypes.data_as(C.c_void_p), _dtype_code(out)))
+        return out
+
+    # -- the loop ---------------------------------------------------------------------------
+    def run(self, niter, compute_w=True, compute_h=True, compute_err=True, early_stop=True):
+        """niter iterations of W-update, H-update, error.  Returns (ferr array, iterations done)."""
+        flags = ((_lib.COMPUTE_W if compute_w else 0) | (_lib.COMPUTE_H if compute_h else 0) |
+                 (_lib.COMPUTE_ERR if compute_err else 0) | (_lib.EARLY_STOP if early_stop else 0))
+        ferr = np.zeros(max(int(niter), 1), dtype=np.float64)
+        done, nf = C.c_int(0), C.c_int(0)
+        _lib.check(self._lib.pymfb_run(self._ctx, int(niter), flags,
+                                       ferr.ctypes.data_as(C.POINTER(C.c_double)),
+                                       C.byref(done), C.byref(nf)))
+        return ferr[:nf.value].copy(), done.value
+
+    def frobenius(self):
+        out = C.c_double(0.0)
+        _lib.check(self._lib.pymfb_frobenius(self._ctx, C.byref(out)))
+        return out.value
+
+    # -- benchmarking helpers -----------------------------------------------------------------
+    def enqueue(self, niter, compute_w=True, compute_h=True, compute_err=True):
+        flags = ((_lib.COMPUTE_W if compute_w else 0) | (_lib.COMPUTE_H if compute_h else 0) |
+                 (_lib.COMPUTE_ERR if compute_err else 0))
+        _lib.check(self._lib.pymfb_enqueue(self._ctx, int(niter), flags))
+
+    def sync(self):
+        _lib.check(self._lib.pymfb_sync(self._ctx))
+
+    def flush_l2(self):
+        _lib.check(self._lib.pymfb_flush_l2(self._ctx))
+
+    def event(self):
+        ev = C.c_void_p()
+        _lib.check(self._lib.pymfb_event_create(C.byref(ev)))
+        return ev
+
+    def record(self, ev):
+        _lib.check(self._lib.pymfb_event_record(self._ctx, ev))
+
+    def elapsed_ms(self, ev0, ev1):
+        ms = C.c_float(0.0)
+        _lib.check(self._lib.pymfb_event_elapsed_ms(ev0, ev1, C.byref(ms)))
+        return ms.value
+
+    def kernel_timing(self, enable):
+        _lib.check(self._lib.pymfb_kernel_timing(self._ctx, 1 if enable else 0))
+
+    def kernel_timing_read(self, which):
+        avg, cnt = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self._lib.pymfb_kernel_timing_read(self._ctx, int(which), C.byref(avg), C.byref(cnt)))
+        return avg.value, cnt.value
+
+    @property
+    def launch_count(self):
+        return int(self._lib.pymfb_launch_count(self._ctx))

@@ -1,0 +1,294 @@
+"""pymf.NMF on B200: host-side mirror of the reference class (pymf/nmf.py:23-202).
+
+Same constructor, ``factorize`` signature, hooks and attributes as the reference, so code
+written against ``pymf.NMF`` runs unchanged; the arithmetic of ``update_w`` (:128-132),
+``update_h`` (:122-126), ``frobenius_norm`` (:100-114) and the ``converged`` early stop
+(:134-139,198-202) runs in libpymfb's sm_100a kernels (see ``engine.py`` / ``include/pymfb.h``).
+There is no CPU path: without the built library or without a B200 every compute call raises.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * device arithmetic is fp32 storage / 3xTF32 or fp32 FMA products / fp64 scalar combines;
+    ``.W`` / ``.H`` come back in the dtype of the host arrays (float64 by default);
+  * X is copied to the GPU on first use and cached (the reference re-reads ``data[:,:]`` on
+    every call); assign ``mdl.data = ...`` to replace it;
+  * sparse ``data`` is rejected by ``factorize`` (the reference only ever returned the
+    ``-123456`` sentinel for it, :109-112).
+"""
+import logging
+
+import numpy as np
+
+from .engine import Engine
+
+__all__ = ["NMF"]
+
+_SENTINEL = -123456      # pymf/nmf.py:112
+
+
+def _is_sparse(a):
+    try:
+        import scipy.sparse
+        return scipy.sparse.issparse(a)
+    except Exception:
+        return False
+
+
+class _Factor(object):
+    """Host array + bookkeeping for one of W / H.
+
+    ``host``       the numpy array the user sees (identity preserved across updates, like the
+                   reference's in-place ``*=`` / ``/=``)
+    ``dev_newer``  the device copy holds newer values than ``host``
+    ``host_dirty`` ``host`` may hold values the device has not seen (assigned, or handed out)
+    """
+    __slots__ = ("host", "dev_newer", "host_dirty")
+
+    def __init__(self, host):
+        self.host = host
+        self.dev_newer = False
+        self.host_dirty = True
+
+
+class NMF(object):
+    """
+    NMF(data, num_bases=4)
+
+    Non-negative Matrix Factorization with Lee-Seung multiplicative updates,
+    ``|data - W*H|`` minimised over non-negative ``W`` (data_dimension x num_bases) and
+    ``H`` (num_bases x num_samples).  Drop-in for ``pymf.NMF`` (pymf/nmf.py:23).
+
+    Extra keyword-only arguments (no reference counterpart):
+      device         CUDA device index (default: LOCAL_RANK or 0)
+      process_group  ``True`` or a ``torch.distributed`` group: ``data`` is this rank's block
+                     of COLUMNS, W is replicated, ``.H`` is the local block, ``.ferr`` is global
+      path           "auto" | "simt" | "tc"  kernel family (default auto)
+    """
+
+    _EPS = 10 ** -8                      # pymf/nmf.py:69
+    _engine_factory = Engine             # tests substitute a checker-backed double here
+
+    def __init__(self, data, num_bases=4, **kw):
+        device = kw.pop("device", None)
+        self._pg = kw.pop("process_group", None)
+        self._path = kw.pop("path", None)
+        if kw:
+            raise TypeError("unexpected keyword arguments: %s" % ", ".join(sorted(kw)))
+
+        def setup_logging():                                   # pymf/nmf.py:73-90
+            self._logger = logging.getLogger("pymf")
+            if len(self._logger.handlers) < 1:
+                ch = logging.StreamHandler()
+                ch.setLevel(logging.DEBUG)
+                ch.setFormatter(logging.Formatter("%(asctime)s [%(levelname)s] %(message)s"))
+                self._logger.addHandler(ch)
+
+        setup_logging()
+        self._engine = None
+        self._x_uploaded = False
+        self._factors = {}
+        self._data = data                                      # by reference, :93
+        self._num_bases = num_bases                            # :94
+        (self._data_dimension, n_local) = self._data.shape     # :97
+        self._n_local = int(n_local)
+        self._col0 = 0
+        self._world, self._rank = 1, 0
+        if self._pg is not None:
+            self._init_distributed()
+        self._num_samples = self._n_global if self._pg is not None else self._n_local
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0")) if self._pg is not None else 0
+        self._device = int(device)
+
+    # ------------------------------------------------------------------ distributed plumbing
+    def _dist(self):
+        import torch.distributed as dist
+        return dist
+
+    def _group(self):
+        return None if self._pg is True else self._pg
+
+    def _init_distributed(self):
+        dist = self._dist()
+        import torch
+        g = self._group()
+        self._world, self._rank = dist.get_world_size(g), dist.get_rank(g)
+        sizes = [None] * self._world
+        dist.all_gather_object(sizes, int(self._n_local), group=g)
+        self._n_global = int(sum(sizes))
+        self._col0 = int(sum(sizes[:self._rank]))
+
+    # ------------------------------------------------------------------ attributes
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._x_uploaded = False
+
+    def _get_factor(self, name):
+        f = self._factors.get(name)
+        if f is None:
+            raise AttributeError("'NMF' object has no attribute '%s'" % name)
+        if f.dev_newer:
+            eng = self._engine
+            fresh = eng.get_w(np.float64) if name == "W" else eng.get_h(np.float64)
+            f.host[...] = fresh                       # in place: `mdl.W is W` stays true
+            f.dev_newer = False
+        f.host_dirty = True                           # handed out: the caller may mutate it
+        return f.host
+
+    def _set_factor(self, name, value):
+        if not (isinstance(value, np.ndarray) and value.dtype.kind == "f" and value.flags.writeable):
+            value = np.array(value, dtype=np.float64)
+        self._factors[name] = _Factor(value)
+
+    W = property(lambda self: self._get_factor("W"), lambda self, v: self._set_factor("W", v),
+                 lambda self: self._factors.pop("W", None))
+    H = property(lambda self: self._get_factor("H"), lambda self, v: self._set_factor("H", v),
+                 lambda self: self._factors.pop("H", None))
+
+    # ------------------------------------------------------------------ engine
+    def _ensure_engine(self):
+        if _is_sparse(self._data):
+            raise TypeError("sparse data is not supported by the NMF multiplicative-update path")
+        if self._engine is None:
+            self._engine = self._engine_factory(self._data_dimension, self._n_local, self._num_bases,
+                                                device=self._device, n_global=self._num_samples,
+                                                col0=self._col0, path=self._path)
+            if self._world > 1:
+                dist = self._dist()
+                box = [self._engine.comm_unique_id() if self._rank == 0 else None]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(self._group(), 0)
+                                           if self._group() is not None else 0, group=self._group())
+                self._engine.comm_init(box[0], self._world, self._rank)
+        if not self._x_uploaded:
+            self._upload_data()
+            self._x_uploaded = True
+        return self._engine
+
+    def _upload_data(self):
+        x = self._data
+        try:
+            import torch
+            if isinstance(x, torch.Tensor):
+                if x.is_cuda:
+                    if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+                        x = x.to(torch.float32).contiguous()
+                        if x.stride(0) % 4:
+                            pad = (-x.shape[1]) % 4
+                            x = torch.nn.functional.pad(x, (0, pad))[:, :self._n_local]
+                    self._engine.bind_x_device(x.data_ptr(), x.stride(0), keepalive=x)
+                    return
+                x = x.numpy()
+        except ImportError:
+            pass
+        if not isinstance(x, np.ndarray):
+            x = np.asarray(x[:, :])                  # h5py-style sources, pymf/nmf.py:110,125,131
+        self._engine.upload_x(x)
+
+    def _sync_to_device(self):
+        eng = self._ensure_engine()
+        for name, setter in (("W", eng.set_w), ("H", eng.set_h)):
+            f = self._factors.get(name)
+            if f is not None and f.host_dirty:
+                setter(f.host)
+                f.host_dirty = False
+                f.dev_newer = False
+        return eng
+
+    def _mark_device_newer(self, name):
+        f = self._factors[name]
+        f.dev_newer = True
+
+    # ------------------------------------------------------------------ reference hooks
+    def frobenius_norm(self):
+        """||data - W H||_F (pymf/nmf.py:100-114); -123456 if W/H are missing or data is sparse."""
+        if "H" in self._factors and "W" in self._factors and not _is_sparse(self._data):
+            return self._sync_to_device().frobenius()
+        return _SENTINEL
+
+    def init_w(self):                                                    # pymf/nmf.py:116-117
+        self.W = np.random.random((self._data_dimension, self._num_bases))
+
+    def init_h(self):                                                    # pymf/nmf.py:119-120
+        if self._world > 1:
+            # same stream as a single-process run with the same seed: draw all of H, keep our columns
+            full = np.random.random((self._num_bases, self._num_samples))
+            self.H = np.ascontiguousarray(full[:, self._col0:self._col0 + self._n_local])
+        else:
+            self.H = np.random.random((self._num_bases, self._num_samples))
+
+    def update_h(self):                                                  # pymf/nmf.py:122-126
+        self._sync_to_device().run(1, compute_w=False, compute_h=True, compute_err=False, early_stop=False)
+        self._mark_device_newer("H")
+
+    def update_w(self):                                                  # pymf/nmf.py:128-132
+        self._sync_to_device().run(1, compute_w=True, compute_h=False, compute_err=False, early_stop=False)
+        self._mark_device_newer("W")
+
+    def converged(self, i):                                              # pymf/nmf.py:134-139
+        derr = np.abs(self.ferr[i] - self.ferr[i - 1]) / self._num_samples
+        return bool(derr < self._EPS)
+
+    def _hooks_overridden(self):
+        cls = type(self)
+        return any(getattr(cls, h) is not getattr(NMF, h)
+                   for h in ("update_w", "update_h", "frobenius_norm", "converged"))
+
+    # ------------------------------------------------------------------ the driver
+    def factorize(self, niter=1, show_progress=False,
+                  compute_w=True, compute_h=True, compute_err=True):
+        """Factorize s.t. WH = data (pymf/nmf.py:141-202).
+
+        niter, show_progress, compute_w, compute_h, compute_err as in the reference.
+        Updates .W, .H and (if compute_err) .ferr.
+        """
+        self._logger.setLevel(logging.INFO if show_progress else logging.ERROR)   # :166-169
+
+        if "W" not in self._factors:                                              # :173-174
+            self.init_w()
+        if "H" not in self._factors:                                              # :176-177
+            self.init_h()
+
+        if self._hooks_overridden():
+            return self._factorize_template(niter, compute_w, compute_h, compute_err)
+
+        eng = self._sync_to_device()
+        ferr, done = eng.run(niter, compute_w=compute_w, compute_h=compute_h,
+                             compute_err=compute_err, early_stop=True)
+        if compute_w and done > 0:
+            self._mark_device_newer("W")
+        if compute_h and done > 0:
+            self._mark_device_newer("H")
+        if compute_err:
+            full = np.zeros(niter)                                                # :179-180
+            full[:len(ferr)] = ferr
+            self.ferr = full[:len(ferr)] if done < niter or len(ferr) < niter else full
+        if show_progress:
+            for i in range(done):                                                 # :191-194
+                if compute_err and i < len(ferr):
+                    self._logger.info('Iteration ' + str(i + 1) + '/' + str(niter) + ' FN:' + str(ferr[i]))
+                else:
+                    self._logger.info('Iteration ' + str(i + 1) + '/' + str(niter))
+
+    def _factorize_template(self, niter, compute_w, compute_h, compute_err):
+        """The reference's template-method loop, used when a subclass overrides a hook."""
+        if compute_err:
+            self.ferr = np.zeros(niter)
+        for i in range(niter):
+            if compute_w:
+                self.update_w()
+            if compute_h:
+                self.update_h()
+            if compute_err:
+                self.ferr[i] = self.frobenius_norm()
+                self._logger.info('Iteration ' + str(i + 1) + '/' + str(niter) + ' FN:' + str(self.ferr[i]))
+            else:
+                self._logger.info('Iteration ' + str(i + 1) + '/' + str(niter))
+            if i > 1 and compute_err:
+                if self.converged(i):
+                    self.ferr = self.ferr[:i]
+                    break

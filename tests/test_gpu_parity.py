@@ -1,0 +1,207 @@
+"""Parity of the CUDA path (through the C ABI / pymf_b200.NMF) against the oracle and the
+committed reference trajectories.  Needs a B200: run with `-m gpu`.
+
+Tolerances are BASELINE.json's: per-iteration W/H within 1e-4 relative Frobenius error of the
+reference's float64 path, ferr within 1e-3 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import pymf_b200
+from oracle import cases, nmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_WH = 1e-4
+TOL_FERR = 1e-3
+
+
+def rel(a, b):
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b)
+
+
+def paths_for(d, n, k):
+    """Kernel families that must serve this shape ('tc' only where it applies)."""
+    e = pymf_b200.Engine(d, n, k)
+    try:
+        X = np.zeros((d, n), dtype=np.float32)
+        e.upload_x(X)
+        auto = e.active_path
+    finally:
+        e.close()
+    return ["simt"] if auto == "simt" else ["simt", "tc"]
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_trajectory_matches_reference_golden(name, golden_dir):
+    """Single-step the engine and compare every kept iteration with the reference's output."""
+    c = cases.CASES[name]
+    g = np.load(os.path.join(golden_dir, "traj_%s.npz" % name))
+    X, W0, H0 = cases.build(name)
+    for path in paths_for(c["d"], c["n"], c["k"]):
+        e = pymf_b200.Engine(c["d"], c["n"], c["k"], path=path)
+        try:
+            e.upload_x(X)
+            e.set_w(W0)
+            e.set_h(H0)
+            ferr = np.zeros(c["niter"])
+            for i in range(c["niter"]):
+                f, done = e.run(1, early_stop=False)
+                ferr[i] = f[0]
+                if (i + 1) in c["keep"]:
+                    assert rel(e.get_w(), g["W_%d" % (i + 1)]) < TOL_WH, (name, path, i)
+                    assert rel(e.get_h(), g["H_%d" % (i + 1)]) < TOL_WH, (name, path, i)
+            assert np.max(np.abs(ferr - g["ferr"]) / g["ferr"]) < TOL_FERR, (name, path)
+            # Frobenius norms of W/H per iteration are not available from single-stepping only at
+            # kept iterations; the final ones are checked through get_w/get_h above.
+        finally:
+            e.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "ragged", "k40"])
+def test_multi_iteration_run_equals_single_stepping(name):
+    """run(niter) (one enqueue, device-side loop state) == niter x run(1)."""
+    c = cases.CASES[name]
+    X, W0, H0 = cases.build(name)
+    e1 = pymf_b200.Engine(c["d"], c["n"], c["k"])
+    e2 = pymf_b200.Engine(c["d"], c["n"], c["k"])
+    try:
+        for e in (e1, e2):
+            e.upload_x(X); e.set_w(W0); e.set_h(H0)
+        f1, done = e1.run(12, early_stop=False)
+        f2 = np.array([e2.run(1, early_stop=False)[0][0] for _ in range(12)])
+        assert done == 12
+        np.testing.assert_allclose(f1, f2, rtol=1e-5)
+        assert rel(e1.get_w(), e2.get_w()) < 1e-5
+        assert rel(e1.get_h(), e2.get_h()) < 1e-5
+    finally:
+        e1.close(); e2.close()
+
+
+def test_reference_test_sequence_on_gpu(golden_dir):
+    """tests/test_pymf.py:69,84-95 through pymf_b200.NMF on the GPU, value-for-value."""
+    g = np.load(os.path.join(golden_dir, "ref_test_3x50.npz"))
+    A = cases.ref_test_matrix()
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    m = pymf_b200.NMF(A, num_bases=4)
+    m.factorize(show_progress=False, niter=20)
+    assert m.ferr.shape == (20,)
+    assert m.ferr[-1] / (A.shape[0] + A.shape[1]) < 0.1
+    assert np.max(np.abs(m.ferr - g["ferr_20"]) / g["ferr_20"]) < TOL_FERR
+    assert rel(m.W, g["W_20"]) < TOL_WH and rel(m.H, g["H_20"]) < TOL_WH
+    m.factorize(compute_h=False)
+    assert rel(m.W, g["W_a"]) < TOL_WH and rel(m.H, g["H_a"]) < TOL_WH
+    assert abs(m.ferr[0] - g["ferr_a"][0]) / g["ferr_a"][0] < TOL_FERR
+    m.factorize(compute_w=False)
+    assert rel(m.H, g["H_b"]) < TOL_WH
+    assert abs(m.ferr[0] - g["ferr_b"][0]) / g["ferr_b"][0] < TOL_FERR
+    old = m.ferr.copy()
+    m.factorize(compute_err=False)
+    np.testing.assert_array_equal(m.ferr, old)
+    assert rel(m.W, g["W_c"]) < TOL_WH and rel(m.H, g["H_c"]) < TOL_WH
+    m.factorize(niter=20)
+    assert rel(m.W, g["W_d"]) < TOL_WH and rel(m.H, g["H_d"]) < TOL_WH
+    assert np.max(np.abs(m.ferr - g["ferr_d"]) / g["ferr_d"]) < TOL_FERR
+    assert isinstance(m.W, np.ndarray) and m.W.dtype == np.float64
+
+
+def test_frobenius_norm_matches_bruteforce():
+    """Trace-identity error vs the oracle's direct ||X - WH|| (pymf/nmf.py:110)."""
+    rng = np.random.RandomState(3)
+    for (d, n, k) in [(64, 96, 8), (300, 1000, 40), (1000, 500, 10)]:
+        X = rng.random_sample((d, n))
+        m = pymf_b200.NMF(X, num_bases=k)
+        m.W = rng.random_sample((d, k))
+        m.H = rng.random_sample((k, n))
+        want = O.frobenius_norm(X, m.W, m.H)
+        assert abs(m.frobenius_norm() - want) / want < TOL_FERR
+
+
+def test_early_stop_state_is_consistent():
+    """Convergence on the 3x50 case: the stop index may differ from float64, the
+    state must be consistent: len(ferr) == iterations_done - 1, W/H are those of the last
+    executed iteration, and the float64 oracle continued from them barely moves."""
+    A = cases.ref_test_matrix()
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    W0, H0 = O.init_wh(3, 50, 4)
+    e = pymf_b200.Engine(3, 50, 4)
+    try:
+        e.upload_x(A); e.set_w(W0); e.set_h(H0)
+        ferr, done = e.run(100000, early_stop=True)
+        assert 3 <= done < 100000 and len(ferr) == done - 1
+        W, H = e.get_w(), e.get_h()
+        # the engine's state equals `done` float64 iterations within tolerance
+        Wr, Hr = W0.copy(), H0.copy()
+        O.factorize(A, Wr, Hr, niter=done, early_stop=False)
+        assert rel(W, Wr) < 5e-3 and rel(H, Hr) < 5e-3     # long run (thousand+ iterations)
+        assert abs(O.frobenius_norm(A, W, H) - ferr[-1]) / ferr[-1] < TOL_FERR
+        # a second run continues from that state (warm start) and does not crash
+        f2, d2 = e.run(3, early_stop=True)
+        assert d2 == 3 and len(f2) == 3
+    finally:
+        e.close()
+
+
+def test_hash_generator_matches_device():
+    d, n, k = 70, 333, 5
+    e = pymf_b200.Engine(d, n, k, n_global=n + 100, col0=60)
+    try:
+        e.gen_x(1234); e.gen_w(5); e.gen_h(6)
+        W = e.get_w(np.float32); H = e.get_h(np.float32)
+        np.testing.assert_array_equal(W, O.gen_matrix(5, d, k))
+        np.testing.assert_array_equal(H, O.gen_matrix(6, k, n + 100, col0=60, ncols=n))
+        # X is checked through one iteration against the oracle on the same block
+        X = O.gen_matrix(1234, d, n + 100, col0=60, ncols=n).astype(np.float64)
+        Wr, Hr = W.astype(np.float64), H.astype(np.float64)
+        fr = O.factorize(X, Wr, Hr, niter=2, early_stop=False)
+        f, _ = e.run(2, early_stop=False)
+        assert rel(e.get_w(), Wr) < TOL_WH and rel(e.get_h(), Hr) < TOL_WH
+        assert np.max(np.abs(f - fr) / fr) < TOL_FERR
+    finally:
+        e.close()
+
+
+def test_device_tensor_input_is_borrowed():
+    import torch
+    rng = np.random.RandomState(1)
+    X = rng.random_sample((128, 256)).astype(np.float32)
+    xt = torch.from_numpy(X).cuda()
+    np.random.seed(2)
+    a = pymf_b200.NMF(xt, num_bases=16)
+    a.factorize(niter=5)
+    np.random.seed(2)
+    b = pymf_b200.NMF(X, num_bases=16)
+    b.factorize(niter=5)
+    np.testing.assert_allclose(a.ferr, b.ferr, rtol=1e-5)
+    Wr, Hr = None, None
+    np.random.seed(2)
+    Wr, Hr = O.init_wh(128, 256, 16)
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=5)
+    assert rel(a.W, Wr) < TOL_WH and rel(a.H, Hr) < TOL_WH
+    assert np.max(np.abs(a.ferr - fr) / fr) < TOL_FERR
+
+
+def test_large_shape_properties():
+    """Size-independent properties at a size the CPU oracle cannot single-step quickly:
+    monotone non-increasing ferr (Lee-Seung), non-negativity, finite values, and the
+    trace-identity error against a brute-force error on a sampled column block."""
+    d, n, k = 4096, 32768, 32
+    e = pymf_b200.Engine(d, n, k)
+    try:
+        e.gen_x(1234); e.gen_w(1235); e.gen_h(1236)
+        ferr, done = e.run(10, early_stop=False)
+        assert done == 10 and np.all(np.isfinite(ferr))
+        assert np.all(np.diff(ferr) <= 1e-5 * ferr[:-1])
+        W = e.get_w(); H = e.get_h()
+        assert W.min() >= 0 and H.min() >= 0 and np.isfinite(W).all() and np.isfinite(H).all()
+        # brute-force error on 2048 sampled columns, scaled comparison of the per-column mean
+        cols = np.arange(0, n, n // 2048)[:2048]
+        Xs = np.stack([O.hash_uniform(1234, np.arange(d, dtype=np.uint64) * np.uint64(n) + np.uint64(c))
+                       for c in cols], axis=1).astype(np.float64)
+        part = np.sum((Xs - W.dot(H[:, cols])) ** 2) / len(cols)
+        full = ferr[-1] ** 2 / n
+        assert abs(part - full) / full < 0.02
+    finally:
+        e.close()
