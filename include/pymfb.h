@@ -44,6 +44,12 @@ typedef struct pymfb_ctx pymfb_ctx;
 
 #define PYMFB_OPT_PATH 1
 
+/* how frobenius_norm is evaluated (pymfb_set_option PYMFB_OPT_ERR_MODE) */
+#define PYMFB_ERR_AUTO   0     /* direct for small problems (d*n*k <= 2^28), trace identity otherwise */
+#define PYMFB_ERR_TRACE  1     /* sqrt(||X||^2 - 2<W, X H^T> + <W^T W, H H^T>): no extra pass over X */
+#define PYMFB_ERR_DIRECT 2     /* sqrt(sum((X - W H)^2)) as written in pymf/nmf.py:110: one more pass */
+#define PYMFB_OPT_ERR_MODE 2
+
 /* Library / ABI version (major*1000 + minor). */
 int pymfb_version(void);
 

@@ -14,6 +14,8 @@ F32, F64 = 0, 1
 COMPUTE_W, COMPUTE_H, COMPUTE_ERR, EARLY_STOP = 1, 2, 4, 8
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 OPT_PATH = 1
+OPT_ERR_MODE = 2
+ERR_AUTO, ERR_TRACE, ERR_DIRECT = 0, 1, 2
 
 _c_ctx = C.c_void_p
 _i64 = C.c_int64

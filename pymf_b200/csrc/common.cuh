@@ -19,6 +19,10 @@ struct DevState {
     double xx;           // ||X||_F^2 over ALL ranks
     double xx_local;     // this rank's share (all-reduced into xx)
     double last_ferr;    // most recent error (pymfb_frobenius)
+    double resid_local;  // direct-residual mode: this rank's sum (X - W H)^2
+    double resid;        // ... summed over ranks
+    unsigned ticket3;    // last-block-done counter of the direct residual
+    unsigned pad_;
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256)
 k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __restrict__ A,
       int64_t n_wa, const float* __restrict__ G, const float* __restrict__ B, int64_t n_gb,
       double* __restrict__ scratch /* 2*ERR_BLOCKS */, double* __restrict__ ferr, int iter,
-      double n_samples, int early_stop) {
+      double n_samples, int early_stop, int direct) {
     if (st->stop) return;
     __shared__ double s_wa[256], s_gb[256];
     __shared__ bool is_last;
@@ -346,7 +346,7 @@ k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __res
             twa += ((volatile double*)scratch)[b];
             tgb += ((volatile double*)scratch)[ERR_BLOCKS + b];
         }
-        double e2 = st->xx - 2.0 * twa + tgb;
+        double e2 = direct ? st->resid : st->xx - 2.0 * twa + tgb;
         double e = sqrt(e2 > 0.0 ? e2 : 0.0);
         st->last_ferr = e;
         st->ticket = 0;
@@ -399,6 +399,85 @@ k_xx(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_
         st->xx_local = t;
         st->xx = t;          // overwritten by the all-reduce when there are several ranks
         st->ticket2 = 0;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Direct residual  sum_{r,c} (X[r][c] - (W H)[r][c])^2  (pymf/nmf.py:110 as written), used for
+// small problems where one more pass is cheap: the trace identity cancels catastrophically
+// when ||X - WH||^2 << ||X||^2 (e.g. the reference's own 3x50 test matrix, which k=4 fits
+// exactly).  Wt = W^T (kp x ldwt, zero padded).  grid.x = column tiles, grid.y = row blocks of KB.
+// fp32 products, fp64 accumulation of squares, deterministic final sum.
+// ---------------------------------------------------------------------------------------
+__global__ void k_transpose_w(const DevState* __restrict__ st, const float* __restrict__ W, int64_t d, int kp,
+                              float* __restrict__ Wt, int64_t ldwt) {
+    if (st->stop) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d * kp) return;
+    const int64_t r = i / kp;
+    const int l = (int)(i % kp);
+    Wt[(int64_t)l * ldwt + r] = W[i];
+}
+
+template <int KB>
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_resid_simt(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
+             const float* __restrict__ Wt, int64_t ldwt, const float* __restrict__ H, int64_t ldh,
+             int64_t d, int64_t n_loc, int kp, double* __restrict__ partial) {
+    if (st->stop) return;
+    constexpr int TK = KB / 8;
+    __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
+    __shared__ __align__(16) float Ls[2][TILE_DK][KB];
+    __shared__ double red[SIMT_THREADS];
+    __shared__ bool is_last;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * TILE_N;
+    const int r0 = blockIdx.y * KB;
+    float acc[TK][4];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    tile_mac<KB>(acc, Wt, ldwt, r0, H, ldh, col0, n_loc, 0, kp, Rs, Ls);   // (W H) tile
+    double s = 0.0;
+    const int64_t col = col0 + tx * 4;
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+        const int64_t r = r0 + ty * TK + i;
+        if (r < d && col < n_loc) {
+            const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + col);
+            float e = x.x - acc[i][0];
+            s += (double)e * (double)e;
+            if (col + 1 < n_loc) { e = x.y - acc[i][1]; s += (double)e * (double)e; }
+            if (col + 2 < n_loc) { e = x.z - acc[i][2]; s += (double)e * (double)e; }
+            if (col + 3 < n_loc) { e = x.w - acc[i][3]; s += (double)e * (double)e; }
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = SIMT_THREADS / 2; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    const unsigned nblocks = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+        __threadfence();
+        is_last = (atomicAdd(&st->ticket3, 1u) == nblocks - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = threadIdx.x; b < nblocks; b += SIMT_THREADS) t += ((volatile double*)partial)[b];
+        red[threadIdx.x] = t;     // fixed assignment of partials to threads -> deterministic
+        __syncthreads();
+        for (int k = SIMT_THREADS / 2; k > 0; k >>= 1) {
+            if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { st->resid_local = red[0]; st->resid = red[0]; st->ticket3 = 0; }
     }
 }
 

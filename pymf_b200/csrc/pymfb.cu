@@ -127,6 +127,12 @@ struct pymfb_ctx {
     float* flush_buf = nullptr;
     size_t flush_bytes = 0;
 
+    // error mode: direct residual for small problems, trace identity otherwise
+    bool err_direct = false;
+    float* Wt = nullptr;           // kp x ldwt (direct mode)
+    int64_t ldwt = 0;
+    double* resid_part = nullptr;
+
     bool ab_valid = false;         // AB matches the current H (and X)
     bool g_valid = false;          // G matches the current W
     bool xx_valid = false;
@@ -146,6 +152,8 @@ struct pymfb_ctx {
     std::vector<cudaEvent_t> ev_pool;
 };
 
+// d * n_local * kp at or below which the error is a direct residual pass (2^28 MACs ~ a few us)
+static const double kDirectErrMaxWork = 268435456.0;
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int grid_for(int64_t count, int block, int cap) {
     int64_t g = (count + block - 1) / block;
@@ -302,9 +310,25 @@ static int launch_xx(pymfb_ctx* c) {
 static int launch_err(pymfb_ctx* c, int iter, bool store, bool early_stop) {
     const float* A = c->AB;
     const float* B = c->AB + c->d * c->kp;
-    k_err<<<ERR_BLOCKS, 256, 0, c->stream>>>(c->st, c->W[c->wcur], A, c->d * c->kp, c->G, B, (int64_t)c->kp * c->kp,
-                                             c->red_scratch, store ? c->ferr_dev : nullptr, iter,
-                                             (double)c->n_glob, early_stop ? 1 : 0);
+    if (c->err_direct) {
+        const int64_t cnt = c->d * c->kp;
+        k_transpose_w<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->st, c->W[c->wcur], c->d, c->kp, c->Wt, c->ldwt);
+        dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)((c->d + c->kb - 1) / c->kb));
+        if (c->kb == 16)
+            k_resid_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part);
+        else
+            k_resid_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        if (c->world > 1)
+            NC(g_nccl.AllReduce(&c->st->resid_local, &c->st->resid, 1, kNcclFloat64, kNcclSum, c->comm, c->stream));
+        k_err<<<1, 256, 0, c->stream>>>(c->st, nullptr, nullptr, 0, nullptr, nullptr, 0, c->red_scratch,
+                                        store ? c->ferr_dev : nullptr, iter, (double)c->n_glob, early_stop ? 1 : 0, 1);
+    } else {
+        k_err<<<ERR_BLOCKS, 256, 0, c->stream>>>(c->st, c->W[c->wcur], A, c->d * c->kp, c->G, B, (int64_t)c->kp * c->kp,
+                                                 c->red_scratch, store ? c->ferr_dev : nullptr, iter,
+                                                 (double)c->n_glob, early_stop ? 1 : 0, 0);
+    }
     c->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -322,7 +346,8 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
     CU(cudaSetDevice(c->device));
     const bool do_w = flags & PYMFB_COMPUTE_W, do_h = flags & PYMFB_COMPUTE_H, do_e = flags & PYMFB_COMPUTE_ERR;
     const bool early = (flags & PYMFB_EARLY_STOP) && do_e;
-    if (do_e && !c->xx_valid) CK(launch_xx(c));
+    const bool trace = do_e && !c->err_direct;   // the trace identity needs ||X||^2, A, B, G
+    if (trace && !c->xx_valid) CK(launch_xx(c));
     for (int i = 0; i < niter; ++i) {
         if (do_w) {
             if (!c->ab_valid) CK(launch_xht(c));      // bootstrap: A, B of the current H
@@ -332,11 +357,11 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
             if (!c->g_valid) CK(launch_gram_w(c));
             CK(launch_h_update(c));
             // A, B of the new H feed the next W update and this iteration's error
-            if (do_e || (do_w && i + 1 < niter)) CK(launch_xht(c));
+            if (trace || (do_w && i + 1 < niter)) CK(launch_xht(c));
         }
         if (do_e) {
-            if (!c->g_valid) CK(launch_gram_w(c));
-            if (!c->ab_valid) CK(launch_xht(c));
+            if (trace && !c->g_valid) CK(launch_gram_w(c));
+            if (trace && !c->ab_valid) CK(launch_xht(c));
             CK(launch_err(c, i, true, early));
         }
     }
@@ -396,6 +421,15 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     }
     CU(cudaMalloc(&c->Gpart, (size_t)c->g_splits * c->kp * c->kp * sizeof(float)));
     CU(cudaMalloc(&c->red_scratch, sizeof(double) * std::max(2 * ERR_BLOCKS, XX_BLOCKS)));
+    // error mode (see k_resid_simt): direct residual while the extra pass is cheap
+    c->err_direct = (double)d * (double)n_local * (double)c->kp <= kDirectErrMaxWork;
+    if (c->err_direct) {
+        c->ldwt = round_up(d, 32);
+        CU(cudaMalloc(&c->Wt, (size_t)c->kp * c->ldwt * sizeof(float)));
+        CU(cudaMemsetAsync(c->Wt, 0, (size_t)c->kp * c->ldwt * sizeof(float), c->stream));
+        const int64_t nb = ((n_local + TILE_N - 1) / TILE_N) * ((d + c->kb - 1) / c->kb);
+        CU(cudaMalloc(&c->resid_part, sizeof(double) * nb));
+    }
     CU(cudaMalloc(&c->st, sizeof(DevState)));
     CU(cudaMemsetAsync(c->st, 0, sizeof(DevState), c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -413,7 +447,7 @@ int pymfb_destroy(pymfb_ctx* c) {
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->AB != c->P) cudaFree(c->AB);
     cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
-    cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own);
+    cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
     for (int i = 0; i < 2; ++i) { cudaFree(c->W[i]); cudaFree(c->H[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
@@ -426,6 +460,21 @@ int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
         if (value < 0 || value > 2) return fail("bad path option %lld", (long long)value);
         c->path_opt = (int)value;
         if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC) CK(tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh)); c->g_valid = false; }
+        return 0;
+    }
+    if (option == PYMFB_OPT_ERR_MODE) {
+        if (value < 0 || value > 2) return fail("bad error mode %lld", (long long)value);
+        CU(cudaSetDevice(c->device));
+        bool direct = value == PYMFB_ERR_DIRECT ||
+                      (value == PYMFB_ERR_AUTO && (double)c->d * (double)c->n_loc * (double)c->kp <= kDirectErrMaxWork);
+        if (direct && !c->Wt) {
+            c->ldwt = round_up(c->d, 32);
+            CU(cudaMalloc(&c->Wt, (size_t)c->kp * c->ldwt * sizeof(float)));
+            CU(cudaMemset(c->Wt, 0, (size_t)c->kp * c->ldwt * sizeof(float)));
+            const int64_t nb = ((c->n_loc + TILE_N - 1) / TILE_N) * ((c->d + c->kb - 1) / c->kb);
+            CU(cudaMalloc(&c->resid_part, sizeof(double) * nb));
+        }
+        c->err_direct = direct;
         return 0;
     }
     return fail("unknown option %d", option);
@@ -648,9 +697,11 @@ int pymfb_frobenius(pymfb_ctx* c, double* out) {
     CK(check_ready(c));
     if (!out) return fail("out is null");
     CU(cudaSetDevice(c->device));
-    if (!c->xx_valid) CK(launch_xx(c));
-    if (!c->g_valid) CK(launch_gram_w(c));
-    if (!c->ab_valid) CK(launch_xht(c));
+    if (!c->err_direct) {
+        if (!c->xx_valid) CK(launch_xx(c));
+        if (!c->g_valid) CK(launch_gram_w(c));
+        if (!c->ab_valid) CK(launch_xht(c));
+    }
     CK(launch_err(c, 0, false, false));
     DevState hs;
     CU(cudaMemcpyAsync(&hs, c->st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));

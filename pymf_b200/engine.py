@@ -51,6 +51,11 @@ class Engine(object):
         code = {"auto": _lib.PATH_AUTO, "simt": _lib.PATH_SIMT, "tc": _lib.PATH_TC}.get(path, path)
         _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_PATH, int(code)))
 
+    def set_err_mode(self, mode):
+        """'auto' | 'trace' (trace identity, no extra pass) | 'direct' (||X - WH|| as written)."""
+        code = {"auto": _lib.ERR_AUTO, "trace": _lib.ERR_TRACE, "direct": _lib.ERR_DIRECT}.get(mode, mode)
+        _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_ERR_MODE, int(code)))
+
     @property
     def active_path(self):
         return {_lib.PATH_SIMT: "simt", _lib.PATH_TC: "tc"}.get(self._lib.pymfb_active_path(self._ctx), "?")

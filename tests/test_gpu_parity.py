@@ -34,8 +34,9 @@ def paths_for(d, n, k):
     return ["simt"] if auto == "simt" else ["simt", "tc"]
 
 
+@pytest.mark.parametrize("err_mode", ["trace", "direct"])
 @pytest.mark.parametrize("name", sorted(cases.CASES))
-def test_trajectory_matches_reference_golden(name, golden_dir):
+def test_trajectory_matches_reference_golden(name, err_mode, golden_dir):
     """Single-step the engine and compare every kept iteration with the reference's output."""
     c = cases.CASES[name]
     g = np.load(os.path.join(golden_dir, "traj_%s.npz" % name))
@@ -43,6 +44,7 @@ def test_trajectory_matches_reference_golden(name, golden_dir):
     for path in paths_for(c["d"], c["n"], c["k"]):
         e = pymf_b200.Engine(c["d"], c["n"], c["k"], path=path)
         try:
+            e.set_err_mode(err_mode)
             e.upload_x(X)
             e.set_w(W0)
             e.set_h(H0)
@@ -117,6 +119,9 @@ def test_frobenius_norm_matches_bruteforce():
         m.H = rng.random_sample((k, n))
         want = O.frobenius_norm(X, m.W, m.H)
         assert abs(m.frobenius_norm() - want) / want < TOL_FERR
+        for mode in ("trace", "direct"):
+            m._engine.set_err_mode(mode)
+            assert abs(m.frobenius_norm() - want) / want < TOL_FERR, mode
 
 
 def test_early_stop_state_is_consistent():
