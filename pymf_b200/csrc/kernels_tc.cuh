@@ -1,13 +1,654 @@
-// kernels_tc.cuh - tcgen05 / TMA kernels (3xTF32) of the streaming passes.  [stub: filled in next]
+// kernels_tc.cuh - tcgen05 / TMEM / TMA kernels (sm_100a) of the two streaming passes.
+//
+//   k_h_update_tc : H <- H * (W^T X) / ((W^T W) H + 1e-9)        pymf/nmf.py:122-126
+//   k_xht_tc      : P_A += X H^T  (feeds the W update, :128-132, and the error, :110)
+//
+// Arithmetic: fp32 storage, every product is a 3xTF32 split  a*b ~= a_hi*b_hi + a_hi*b_lo +
+// a_lo*b_hi  (a_hi = a with the low 13 mantissa bits cleared, a_lo = a - a_hi, exact in fp32),
+// accumulated in fp32 in TMEM.  The two a_hi terms are ONE MMA of width N = 2k against the
+// concatenated operand [b_hi | b_lo]; the a_lo term is a second MMA of width k that accumulates
+// into the "small terms" half, so every element of X crosses shared memory -> tensor core twice
+// per pass instead of three times.  hi + small halves are added in the epilogue.
+//
+// Data movement: X (and H) tiles arrive by TMA (cp.async.bulk.tensor, 128B swizzle) into a
+// multi-stage mbarrier ring; 4 "split" warps derive the lo tiles in shared memory; one thread
+// issues tcgen05.mma; 4 epilogue warps read the accumulators with tcgen05.ld.  Persistent CTAs
+// (one per SM) loop over column tiles / (row block, column range) tasks.
+//
+// Layout facts used below (sm_100 UMMA canonical layouts, fp32/tf32 elements, 128B swizzle):
+//   MN-major operand: smem = [k rows][32 elements = 128 B]; 8 rows = one 1024 B swizzle atom;
+//                     SBO = byte stride between 8-row groups, LBO = byte stride between
+//                     32-element chunks along M/N.  One MMA (K = 8) consumes one 8-row group.
+//   K-major operand : smem = [m rows][32 elements along K = 128 B]; SBO = stride between 8-row
+//                     groups (1024 B); one MMA consumes 32 B of each row (start address + 32 B).
+//   Both are exactly what a TMA box of 32 fp32 x R rows with SWIZZLE_128B writes.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <string>
+
 #include "common.cuh"
+
+#ifndef PYMFB_TC_RAW_HI
+#define PYMFB_TC_RAW_HI 0   // 1: feed the raw fp32 tile as the hi operand (relies on the MMA ignoring
+                            //    the low 13 mantissa bits); 0: write the masked hi tile back explicitly
+#endif
+
 namespace pymfb {
-struct TcPlan { bool ready = false; };
-inline bool tc_supported(int64_t, int64_t, int, int64_t, const float*, std::string* why) { *why = "tcgen05 kernels not built yet"; return false; }
-inline int tc_plan(TcPlan&, int, int, int64_t, int64_t, int, int, const float*, int64_t, int64_t) { return 1; }
-inline void tc_release(TcPlan&) {}
-inline int tc_after_gram(TcPlan&, const DevState*, const float*, const float*, cudaStream_t, int64_t*) { return 1; }
-inline int tc_h_update(TcPlan&, const DevState*, const float*, int64_t, const float*, float*, cudaStream_t, int64_t*) { return 1; }
-inline int tc_xht(TcPlan&, const DevState*, const float*, int64_t, const float*, float*, cudaStream_t, int64_t*) { return 1; }
+namespace tc {
+
+constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
+constexpr int R1 = 32;                // rows (contraction) per stage of the H-update pass
+constexpr int TILE_COLS = 128;        // columns per tile = UMMA M of the H-update pass
+constexpr int XSTAGE_BYTES = 128 * 32 * 4;   // 16 KB: 128 x 32 fp32 in either orientation
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// descriptors
+// ---------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// hi/lo split of a float4 (hi = low 13 mantissa bits cleared; lo = exact remainder)
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+// split `nvec` float4 of a stage buffer: raw -> (hi in place unless RAW_HI) + lo buffer
+__device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, int tid, int nthreads) {
+    for (int i = tid; i < nvec; i += nthreads) {
+        float4 v = raw[i], h, l;
+        split4(v, h, l);
+#if !PYMFB_TC_RAW_HI
+        raw[i] = h;
+#endif
+        lo[i] = l;
+    }
+}
+
+template <int KP>
+struct HCfg {   // H-update pass
+    static constexpr int NCH = 2 * KP / 32;                         // 32-column chunks of [hi | lo]
+    static constexpr int WSTAGE_BYTES = NCH * R1 * 128;             // R1 rows x 2KP fp32
+    static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + WSTAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int ACC_COLS = 4 * KP;                         // [C hi | C small | D hi | D small]
+    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
+    static_assert(STAGES >= 2, "not enough shared memory for two stages");
+};
+
+// ---------------------------------------------------------------------------------------------
+// H-update pass.  Per 128-column tile:  TMEM acc = [ X^T W_hi | X^T W_lo + X_lo^T W_hi | H^T G_hi | ... ]
+//   lanes = columns of the tile, TMEM columns = basis index.  The contraction runs over the d rows
+//   of X (operands X tile / [W_hi | W_lo]) and then over the kp rows of H (operands H tile /
+//   [G_hi | G_lo]) through the same stage ring.
+// ---------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(THREADS, 1)
+k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+              const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
+              const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
+              int64_t ldh, int d, int n_loc, int num_tiles) {
+    using Cfg = HCfg<KP>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    // barriers: full[S], ready[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int nd = (d + R1 - 1) / R1;            // stages over the rows of X
+    const int nit = nd + KP / R1;                // + stages over the rows of H (for G H)
+    auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+    auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
+    auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int col0 = tile * TILE_COLS;
+                for (int it = 0; it < nit; ++it) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::WSTAGE_BYTES);
+                    const bool xphase = it < nd;
+                    const int r0 = (xphase ? it : it - nd) * R1;
+                    const CUtensorMap* ma = xphase ? &mapX : &mapH;
+                    const CUtensorMap* mb = xphase ? &mapW : &mapG;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tma_load_2d(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0);
+#pragma unroll
+                    for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
+            constexpr uint32_t idesc_h = make_idesc(128, KP, 1, 1);
+            int s = 0; uint32_t ph = 0; int lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt % Cfg::ACC_STAGES;
+                const uint32_t aph = (uint32_t)(lt / Cfg::ACC_STAGES) & 1u;
+                mbar_wait(tempty_bar(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t acc_base = tmem_base + acc * Cfg::ACC_COLS;
+                for (int it = 0; it < nit; ++it) {
+                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(ready_bar(s), ph);
+                    tc_fence_after();
+                    const bool xphase = it < nd;
+                    const uint32_t dcol = acc_base + (xphase ? 0 : 2 * KP);
+                    const bool first = (it == 0) || (it == nd);
+#pragma unroll
+                    for (int kg = 0; kg < R1 / 8; ++kg) {
+                        const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 1024);
+                        const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 1024);
+                        const uint64_t b = make_desc(wch(s) + kg * 1024, R1 * 128, 1024);
+                        umma_tf32(dcol, a_hi, b, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                        umma_tf32(dcol + KP, a_lo, b, idesc_h, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== split warps: lo tiles (and masked hi) of the X / H operand =====
+        const int tid_s = threadIdx.x - 64;
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; it < nit; ++it) {
+                mbar_wait(full_bar(s), ph);
+                float4* raw = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + XSTAGE_BYTES);
+                split_buffer(raw, lo, XSTAGE_BYTES / 16, tid_s, 128);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_bar(s));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> H update -> global =====
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt % Cfg::ACC_STAGES;
+            const uint32_t aph = (uint32_t)(lt / Cfg::ACC_STAGES) & 1u;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const int col = tile * TILE_COLS + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
+#pragma unroll 1
+            for (int j0 = 0; j0 < KP; j0 += 16) {
+                float ch[16], cl[16], dh[16], dl[16];
+                tmem_ld16(taddr + j0, ch);
+                tmem_ld16(taddr + KP + j0, cl);
+                tmem_ld16(taddr + 2 * KP + j0, dh);
+                tmem_ld16(taddr + 3 * KP + j0, dl);
+                tmem_ld_wait();
+                if (col < n_loc) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int64_t o = (int64_t)(j0 + j) * ldh + col;
+                        const float h = Hc[o];
+                        Hn[o] = (h * (ch[j] + cl[j])) / ((dh[j] + dl[j]) + kEpsDenom);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KP>
+struct XCfg {   // X H^T pass
+    static constexpr int HSTAGE_BYTES = 2 * KP * 128;               // [H hi rows | H lo rows] x 32 cols
+    static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + HSTAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int ACC_COLS = 2 * KP;                         // [hi | small]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
+};
+
+// ---------------------------------------------------------------------------------------------
+// X H^T pass.  Task = (block of 128 rows of X, range of columns); TMEM acc (lanes = rows of X,
+// columns = basis index) = [ X H_hi^T | X H_lo^T + X_lo H_hi^T ], flushed with fp32 atomics.
+// ---------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(THREADS, 1)
+k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
+         const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
+         int cols_per_task, int num_rb, int num_tasks) {
+    using Cfg = XCfg<KP>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapH);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+    auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
+    auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
+    auto task_cols = [&](int task, int& c_begin, int& c_end) {
+        const int cs = task / num_rb;
+        c_begin = cs * cols_per_task;
+        c_end = min(n_loc, c_begin + cols_per_task);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+                int c_begin, c_end;
+                task_cols(task, c_begin, c_end);
+                const int row0 = (task % num_rb) * 128;
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
+                    tma_load_2d(xraw(s), &mapX, full_bar(s), c0, row0);
+                    tma_load_2d(hch(s), &mapH, full_bar(s), c0, 0);
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
+            constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
+            int s = 0; uint32_t ph = 0; int lt = 0;
+            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x, ++lt) {
+                int c_begin, c_end;
+                task_cols(task, c_begin, c_end);
+                const int acc = lt & 1;
+                const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + acc * Cfg::ACC_COLS;
+                bool first = true;
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(ready_bar(s), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
+                        const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
+                        const uint64_t b = make_desc(hch(s) + ks * 32, 16, 1024);
+                        umma_tf32(dcol, a_hi, b, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                        umma_tf32(dcol + KP, a_lo, b, idesc_h, 1u);
+                    }
+                    first = false;
+                    umma_commit(empty_bar(s));
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+    } else if (warp < 6) {
+        const int tid_s = threadIdx.x - 64;
+        int s = 0; uint32_t ph = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin, c_end;
+            task_cols(task, c_begin, c_end);
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                mbar_wait(full_bar(s), ph);
+                uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
+                split_buffer(reinterpret_cast<float4*>(stage), reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
+                             XSTAGE_BYTES / 16, tid_s, 128);
+                split_buffer(reinterpret_cast<float4*>(stage + 2 * XSTAGE_BYTES),
+                             reinterpret_cast<float4*>(stage + 2 * XSTAGE_BYTES + KP * 128), KP * 128 / 16, tid_s, 128);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_bar(s));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int lt = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const int row = (task % num_rb) * 128 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
+#pragma unroll 1
+            for (int j0 = 0; j0 < KP; j0 += 16) {
+                float hi[16], lo[16];
+                tmem_ld16(taddr + j0, hi);
+                tmem_ld16(taddr + KP + j0, lo);
+                tmem_ld_wait();
+                if (row < d) {
+                    float* dst = P + (int64_t)row * KP + j0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j, hi[j] + lo[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// [hi | lo] split of a small row-major matrix: src rows x kp -> dst rows x 2kp   (W and G)
+__global__ void k_split_hilo(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int kp,
+                             float* __restrict__ dst) {
+    if (st->stop) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * kp) return;
+    const int64_t r = i / kp;
+    const int c = (int)(i % kp);
+    const float v = src[i];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    dst[r * 2 * kp + c] = hi;
+    dst[r * 2 * kp + kp + c] = v - hi;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side: plan (tensor maps, split buffers) and launchers
+// ---------------------------------------------------------------------------------------------
+struct TcPlan {
+    bool ready = false;
+    int device = 0, sm_count = 148;
+    int64_t d = 0, n_loc = 0, ldx = 0, ldh = 0;
+    int k = 0, kp = 0;
+    const float* X = nullptr;
+    const float* Hbuf[2] = {nullptr, nullptr};
+    float* Wsplit = nullptr;   // d x 2kp  [W_hi | W_lo]
+    float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
+    CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
+    int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
+    std::string err;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 2-D fp32 row-major matrix (rows x cols, leading dimension ld), box = 32 columns x box_rows, 128B swizzle,
+// out-of-bounds elements read as zero.
+inline bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     std::string* err) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return false; }
+    return true;
+}
+
+inline bool tc_supported(int64_t d, int64_t n_loc, int kp, int64_t ldx, const float* X, std::string* why) {
+    if (kp % 32 != 0 || kp < 32 || kp > 128) { *why = "k (padded) must be 32..128 in steps of 32"; return false; }
+    if (ldx % 4 != 0 || ((uintptr_t)X & 15) != 0) { *why = "X must be 16-byte aligned with ld % 4 == 0"; return false; }
+    if (d >= (1LL << 31) || n_loc >= (1LL << 31) - 256) { *why = "dimension too large"; return false; }
+    if (d < 64 || n_loc < 128) { *why = "problem too small for the tensor-core tiles"; return false; }
+    return true;
+}
+
+template <int KP>
+inline int tc_set_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(tc::k_h_update_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::HCfg<KP>::SMEM_BYTES);
+    if (e != cudaSuccess) return 1;
+    e = cudaFuncSetAttribute(tc::k_xht_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::XCfg<KP>::SMEM_BYTES);
+    return e == cudaSuccess ? 0 : 1;
+}
+
+inline void tc_release(TcPlan& p) {
+    if (p.Wsplit) cudaFree(p.Wsplit);
+    if (p.Gsplit) cudaFree(p.Gsplit);
+    p.Wsplit = p.Gsplit = nullptr;
+    p.ready = false;
+}
+
+inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc, int k, int kp, const float* X,
+                   int64_t ldx, int64_t ldh, const float* H0, const float* H1) {
+    tc_release(p);
+    p.device = device; p.sm_count = sm_count; p.d = d; p.n_loc = n_loc; p.k = k; p.kp = kp; p.X = X; p.ldx = ldx; p.ldh = ldh;
+    p.Hbuf[0] = H0; p.Hbuf[1] = H1;
+    if (cudaMalloc(&p.Wsplit, (size_t)d * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Wsplit failed"; return 1; }
+    if (cudaMalloc(&p.Gsplit, (size_t)kp * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Gsplit failed"; return 1; }
+    bool ok = true;
+    ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, &p.err);
+    ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, &p.err);
+    ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * kp, 2 * kp, tc::R1, &p.err);
+    ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, &p.err);
+    for (int i = 0; i < 2; ++i) {
+        ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, &p.err);
+        ok = ok && make_map(&p.mapH_x[i], p.Hbuf[i], kp, n_loc, ldh, kp, &p.err);
+    }
+    if (!ok) return 1;
+    int rc = kp == 32 ? tc_set_attrs<32>() : kp == 64 ? tc_set_attrs<64>() : kp == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
+    if (rc) { p.err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; return 1; }
+    p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
+    // X H^T tasks: (row block, column range); ~4 tasks per SM, each a multiple of 32 columns
+    p.x_rb = (int)((d + 127) / 128);
+    const int64_t chunks = (n_loc + 31) / 32;
+    int64_t splits = std::max<int64_t>(1, (4LL * sm_count + p.x_rb - 1) / p.x_rb);
+    splits = std::min(splits, chunks);
+    const int64_t chunks_per = (chunks + splits - 1) / splits;
+    p.x_cols_per_task = (int)(chunks_per * 32);
+    splits = (chunks + chunks_per - 1) / chunks_per;
+    p.x_tasks = (int)(splits * p.x_rb);
+    p.ready = true;
+    return 0;
+}
+
+// refresh [W_hi | W_lo] and [G_hi | G_lo] after W / G changed
+inline int tc_after_gram(TcPlan& p, const DevState* st, const float* W, const float* G, cudaStream_t stream, int64_t* launches) {
+    const int64_t nw = p.d * p.kp, ng = (int64_t)p.kp * p.kp;
+    tc::k_split_hilo<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(st, W, p.d, p.kp, p.Wsplit);
+    tc::k_split_hilo<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(st, G, p.kp, p.kp, p.Gsplit);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+template <int KP>
+inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
+    const int grid = std::min(p.h_tiles, p.sm_count);
+    tc::k_h_update_tc<KP><<<grid, tc::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles);
+}
+inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
+    const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    switch (p.kp) {
+        case 32: tc_launch_h<32>(p, st, hsrc, Hn, stream); break;
+        case 64: tc_launch_h<64>(p, st, hsrc, Hn, stream); break;
+        case 96: tc_launch_h<96>(p, st, hsrc, Hn, stream); break;
+        default: tc_launch_h<128>(p, st, hsrc, Hn, stream); break;
+    }
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+template <int KP>
+inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
+    const int grid = std::min(p.x_tasks, p.sm_count);
+    tc::k_xht_tc<KP><<<grid, tc::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks);
+}
+inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
+    const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    switch (p.kp) {
+        case 32: tc_launch_x<32>(p, st, hsrc, P, stream); break;
+        case 64: tc_launch_x<64>(p, st, hsrc, P, stream); break;
+        case 96: tc_launch_x<96>(p, st, hsrc, P, stream); break;
+        default: tc_launch_x<128>(p, st, hsrc, P, stream); break;
+    }
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 }  // namespace pymfb

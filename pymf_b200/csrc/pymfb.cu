@@ -205,7 +205,7 @@ static int launch_gram_w(pymfb_ctx* c) {
     k_sum_partials<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->st, c->Gpart, c->g_splits, cnt, c->G);
     c->launches += 2;
     CU(cudaGetLastError());
-    if (c->path == PYMFB_PATH_TC) CK(tc_after_gram(c->tc, c->st, c->W[c->wcur], c->G, c->stream, &c->launches));
+    if (c->path == PYMFB_PATH_TC && tc_after_gram(c->tc, c->st, c->W[c->wcur], c->G, c->stream, &c->launches)) return fail("split kernel launch failed");
     c->g_valid = true;
     return 0;
 }
@@ -228,7 +228,7 @@ static int launch_h_update(pymfb_ctx* c) {
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 0, &e0, &e1));
     if (c->path == PYMFB_PATH_TC) {
-        CK(tc_h_update(c->tc, c->st, c->X, c->ldx, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches));
+        if (tc_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("tcgen05 H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
         if (c->kb == 16)
@@ -266,7 +266,7 @@ static int launch_xht(pymfb_ctx* c) {
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 1, &e0, &e1));
     if (c->path == PYMFB_PATH_TC) {
-        CK(tc_xht(c->tc, c->st, c->X, c->ldx, Hc, c->P, c->stream, &c->launches));
+        if (tc_xht(c->tc, c->st, Hc, c->P, c->stream, &c->launches)) return fail("tcgen05 X.H^T launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         int64_t cps; unsigned ns;
         xht_splits(c, c->d, &cps, &ns);
@@ -459,7 +459,7 @@ int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
     if (option == PYMFB_OPT_PATH) {
         if (value < 0 || value > 2) return fail("bad path option %lld", (long long)value);
         c->path_opt = (int)value;
-        if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC) CK(tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh)); c->g_valid = false; }
+        if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC && tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1])) return fail("tcgen05 plan failed: %s", c->tc.err.c_str()); c->g_valid = false; }
         return 0;
     }
     if (option == PYMFB_OPT_ERR_MODE) {
@@ -505,7 +505,7 @@ int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
 static int data_changed(pymfb_ctx* c) {
     c->ab_valid = false; c->xx_valid = false;
     CK(resolve_path(c));
-    if (c->path == PYMFB_PATH_TC) CK(tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh));
+    if (c->path == PYMFB_PATH_TC && tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1])) return fail("tcgen05 plan failed: %s", c->tc.err.c_str());
     c->g_valid = false;
     return 0;
 }

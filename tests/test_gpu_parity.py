@@ -210,3 +210,35 @@ def test_large_shape_properties():
         assert abs(part - full) / full < 0.02
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 32), (300, 1000, 40), (512, 640, 128), (1024, 4096, 64),
+                                   (4096, 2048, 32), (200, 3000, 96), (130, 131, 17)])
+def test_tensor_core_path_matches_fp32_path(shape):
+    """tcgen05 3xTF32 kernels vs the fp32 CUDA-core kernels vs the float64 oracle, 3 iterations,
+    including shapes whose d / n / k are not multiples of the tile sizes."""
+    d, n, k = shape
+    rng = np.random.RandomState(d + n + k)
+    X = rng.random_sample((d, n)).astype(np.float32)
+    W0 = rng.random_sample((d, k))
+    H0 = rng.random_sample((k, n))
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=3, early_stop=False)
+    res = {}
+    for path in ("simt", "tc"):
+        e = pymf_b200.Engine(d, n, k, path=path)
+        try:
+            e.set_err_mode("trace")
+            e.upload_x(X); e.set_w(W0); e.set_h(H0)
+            f, done = e.run(3, early_stop=False)
+            assert e.active_path == path
+            res[path] = (e.get_w(), e.get_h(), f)
+        finally:
+            e.close()
+        W, H, f = res[path]
+        assert rel(W, Wr) < TOL_WH, (path, rel(W, Wr))
+        assert rel(H, Hr) < TOL_WH, (path, rel(H, Hr))
+        assert np.max(np.abs(f - fr) / fr) < TOL_FERR, path
+    # the two kernel families agree far below the tolerance (3xTF32 ~ fp32 accuracy)
+    assert rel(res["tc"][0], res["simt"][0]) < 2e-5
+    assert rel(res["tc"][1], res["simt"][1]) < 2e-5
