@@ -16,12 +16,13 @@
 // (one per SM) loop over column tiles / (row block, column range) tasks.
 //
 // Layout facts used below (sm_100 UMMA canonical layouts, fp32/tf32 elements, 128B swizzle):
-//   MN-major operand: smem = [k rows][32 elements = 128 B]; 8 rows = one 1024 B swizzle atom;
-//                     SBO = byte stride between 8-row groups, LBO = byte stride between
-//                     32-element chunks along M/N.  One MMA (K = 8) consumes one 8-row group.
+//   MN-major operand: smem = [k rows][32 elements = 128 B], "128B swizzle with 32B atoms" (the only
+//                     MN-major layout tf32 supports): 4 rows = one 512 B swizzle atom; SBO = byte
+//                     stride between 4-row groups, LBO = byte stride between 32-element chunks
+//                     along M/N.  One MMA (K = 8) consumes two 4-row groups.
 //   K-major operand : smem = [m rows][32 elements along K = 128 B]; SBO = stride between 8-row
 //                     groups (1024 B); one MMA consumes 32 B of each row (start address + 32 B).
-//   Both are exactly what a TMA box of 32 fp32 x R rows with SWIZZLE_128B writes.
+//   Both are exactly what a TMA box of 32 fp32 x R rows writes (SWIZZLE_128B_ATOM_32B resp. SWIZZLE_128B).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -38,7 +39,6 @@
 namespace pymfb {
 namespace tc {
 
-constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int R1 = 32;                // rows (contraction) per stage of the H-update pass
 constexpr int TILE_COLS = 128;        // columns per tile = UMMA M of the H-update pass
 constexpr int XSTAGE_BYTES = 128 * 32 * 4;   // 16 KB: 128 x 32 fp32 in either orientation
@@ -126,13 +126,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B - the only layout the hardware
+// accepts for MN-major tf32 operands (128 B rows whose four 32 B chunks are XOR-permuted by row % 4;
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; swizzle atom = 4 rows = 512 B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
@@ -162,6 +165,14 @@ __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, 
     }
 }
 
+constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "segments" below)
+
+// Segments.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, so a long chain of
+// accumulating MMAs drifts low by ~4.5e-8 per MMA (measured: 2.7e-5 relative after the 512 MMAs of
+// d = 4096).  Both passes therefore cut the contraction into segments of SEG_STAGES stages
+// (32 MMAs per chain): the MMA thread alternates between two TMEM buffers, and the epilogue warps
+// drain each finished segment into fp32 registers with round-to-nearest adds while the next
+// segment is being accumulated.
 template <int KP>
 struct HCfg {   // H-update pass
     static constexpr int NCH = 2 * KP / 32;                         // 32-column chunks of [hi | lo]
@@ -169,25 +180,30 @@ struct HCfg {   // H-update pass
     static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + WSTAGE_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-    static constexpr int ACC_COLS = 4 * KP;                         // [C hi | C small | D hi | D small]
-    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int SEG_COLS = 2 * KP;                         // [hi | small] per segment buffer
+    static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;               // 2 warps per TMEM lane quarter for wide k
+    static constexpr int NJ = KP / (EPI_WARPS / 4);                 // basis columns per epilogue thread
+    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
     static_assert(STAGES >= 2, "not enough shared memory for two stages");
+    static_assert(NJ % 16 == 0, "epilogue column split must be a multiple of 16");
 };
 
 // ---------------------------------------------------------------------------------------------
-// H-update pass.  Per 128-column tile:  TMEM acc = [ X^T W_hi | X^T W_lo + X_lo^T W_hi | H^T G_hi | ... ]
-//   lanes = columns of the tile, TMEM columns = basis index.  The contraction runs over the d rows
-//   of X (operands X tile / [W_hi | W_lo]) and then over the kp rows of H (operands H tile /
-//   [G_hi | G_lo]) through the same stage ring.
+// H-update pass.  Per 128-column tile (TMEM lanes = columns of the tile, TMEM columns = basis index):
+//   C segments:  [ X^T W_hi | X^T W_lo + X_lo^T W_hi ]  over 256-row slices of X  -> summed in registers
+//   D segment :  [ H^T G_hi | H^T G_lo + H_lo^T G_hi ]  over the kp rows of H
+//   epilogue  :  Hn = H * C / (D + 1e-9)
+// X/W and H/G stages travel through the same TMA -> split -> MMA ring.
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: hi/lo split, warps 6..: epilogue.
 // ---------------------------------------------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(HCfg<KP>::THREADS, 1)
 k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
-              int64_t ldh, int d, int n_loc, int num_tiles) {
+              int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
     using Cfg = HCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -207,7 +223,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -248,32 +264,36 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 1, 1);
-            int s = 0; uint32_t ph = 0; int lt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-                const int acc = lt % Cfg::ACC_STAGES;
-                const uint32_t aph = (uint32_t)(lt / Cfg::ACC_STAGES) & 1u;
-                mbar_wait(tempty_bar(acc), aph ^ 1);
-                tc_fence_after();
-                const uint32_t acc_base = tmem_base + acc * Cfg::ACC_COLS;
-                for (int it = 0; it < nit; ++it) {
-                    mbar_wait(full_bar(s), ph);
-                    mbar_wait(ready_bar(s), ph);
+            int s = 0; uint32_t ph = 0; uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int it = 0;
+                while (it < nit) {
+                    const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
+                    const uint32_t b = g & 1u;
+                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
-                    const bool xphase = it < nd;
-                    const uint32_t dcol = acc_base + (xphase ? 0 : 2 * KP);
-                    const bool first = (it == 0) || (it == nd);
+                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                    bool first = true;
+                    for (; it < seg_end; ++it) {
+                        mbar_wait(full_bar(s), ph);
+                        mbar_wait(ready_bar(s), ph);
+                        tc_fence_after();
 #pragma unroll
-                    for (int kg = 0; kg < R1 / 8; ++kg) {
-                        const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 1024);
-                        const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 1024);
-                        const uint64_t b = make_desc(wch(s) + kg * 1024, R1 * 128, 1024);
-                        umma_tf32(dcol, a_hi, b, idesc_hl, (first && kg == 0) ? 0u : 1u);
-                        umma_tf32(dcol + KP, a_lo, b, idesc_h, 1u);
+                        for (int kg = 0; kg < R1 / 8; ++kg) {
+                            // one MMA (K = 8) = two 4-row swizzle atoms (SBO = 512 B); 32-column chunks LBO apart
+                            const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 512, 1);
+                            const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 512, 1);
+                            const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
+                            umma_tf32(dcol, a_hi, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                            umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                        }
+                        first = false;
+                        umma_commit(empty_bar(s));
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(empty_bar(s));
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    umma_commit(tfull_bar(b));
+                    ++g;
                 }
-                umma_commit(tfull_bar(acc));
             }
         }
     } else if (warp < 6) {
@@ -293,36 +313,65 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> H update -> global =====
+        // ===== epilogue warps: drain segments into registers, then the H update =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int acc = lt % Cfg::ACC_STAGES;
-            const uint32_t aph = (uint32_t)(lt / Cfg::ACC_STAGES) & 1u;
-            mbar_wait(tfull_bar(acc), aph);
-            tc_fence_after();
-            const int col = tile * TILE_COLS + q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
-#pragma unroll 1
-            for (int j0 = 0; j0 < KP; j0 += 16) {
-                float ch[16], cl[16], dh[16], dl[16];
-                tmem_ld16(taddr + j0, ch);
-                tmem_ld16(taddr + KP + j0, cl);
-                tmem_ld16(taddr + 2 * KP + j0, dh);
-                tmem_ld16(taddr + 3 * KP + j0, dl);
-                tmem_ld_wait();
-                if (col < n_loc) {
+        const int jbase = ((warp - 6) >> 2) * Cfg::NJ;   // basis columns [jbase, jbase + NJ) of this warp
+        const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            float creg[Cfg::NJ];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int64_t o = (int64_t)(j0 + j) * ldh + col;
-                        const float h = Hc[o];
-                        Hn[o] = (h * (ch[j] + cl[j])) / ((dh[j] + dl[j]) + kEpsDenom);
+            for (int j = 0; j < Cfg::NJ; ++j) creg[j] = 0.f;
+            for (int seg = 0; seg < nsegC; ++seg, ++g) {
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
+#pragma unroll
+                for (int j0 = 0; j0 < Cfg::NJ; j0 += 16) {
+                    float hi[16], sm[16];
+                    tmem_ld16(taddr + j0, hi);
+                    tmem_ld16(taddr + KP + j0, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+            }
+            {   // D segment + H update
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
+                const int col = tile * TILE_COLS + q * 32 + lane;
+#pragma unroll
+                for (int j0 = 0; j0 < Cfg::NJ; j0 += 16) {
+                    float dh[16], dl[16];
+                    tmem_ld16(taddr + j0, dh);
+                    tmem_ld16(taddr + KP + j0, dl);
+                    tmem_ld_wait();
+                    if (dbg != nullptr && tile == 0) {   // raw sums of tile 0 (tests/tc_probe.cu)
+                        float* o = dbg + (size_t)(q * 32 + lane) * (2 * KP) + jbase + j0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { o[j] = creg[j0 + j]; o[KP + j] = dh[j] + dl[j]; }
+                    }
+                    if (col < n_loc) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int64_t o = (int64_t)(jbase + j0 + j) * ldh + col;
+                            const float h = Hc[o];
+                            Hn[o] = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+                ++g;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
     }
     tc_fence_before();
@@ -336,20 +385,25 @@ struct XCfg {   // X H^T pass
     static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + HSTAGE_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-    static constexpr int ACC_COLS = 2 * KP;                         // [hi | small]
+    static constexpr int SEG_COLS = 2 * KP;                         // [hi | small]
+    static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;
+    static constexpr int NJ = KP / (EPI_WARPS / 4);
+    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
+    static_assert(NJ % 16 == 0, "epilogue column split must be a multiple of 16");
 };
 
 // ---------------------------------------------------------------------------------------------
-// X H^T pass.  Task = (block of 128 rows of X, range of columns); TMEM acc (lanes = rows of X,
-// columns = basis index) = [ X H_hi^T | X H_lo^T + X_lo H_hi^T ], flushed with fp32 atomics.
+// X H^T pass.  Task = (block of 128 rows of X, range of columns).  TMEM lanes = rows of X, TMEM
+// columns = basis index; segments [ X H_hi^T | X H_lo^T + X_lo H_hi^T ] over 256 columns each are
+// summed in registers and flushed once per task with fp32 atomics into P (d x KP).
 // ---------------------------------------------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
-         int cols_per_task, int num_rb, int num_tasks) {
+         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg) {
     using Cfg = XCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -368,7 +422,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapH);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -380,24 +434,25 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
     auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
-    auto task_cols = [&](int task, int& c_begin, int& c_end) {
+    auto task_chunks = [&](int task, int& c_begin) {     // number of 32-column stages of a task
         const int cs = task / num_rb;
         c_begin = cs * cols_per_task;
-        c_end = min(n_loc, c_begin + cols_per_task);
+        const int c_end = min(n_loc, c_begin + cols_per_task);
+        return (c_end - c_begin + 31) / 32;
     };
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-                int c_begin, c_end;
-                task_cols(task, c_begin, c_end);
+                int c_begin;
+                const int nch = task_chunks(task, c_begin);
                 const int row0 = (task % num_rb) * 128;
-                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                for (int ch = 0; ch < nch; ++ch) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
-                    tma_load_2d(xraw(s), &mapX, full_bar(s), c0, row0);
-                    tma_load_2d(hch(s), &mapH, full_bar(s), c0, 0);
+                    tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
+                    tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -406,42 +461,46 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         if (lane == 0) {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
-            int s = 0; uint32_t ph = 0; int lt = 0;
-            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x, ++lt) {
-                int c_begin, c_end;
-                task_cols(task, c_begin, c_end);
-                const int acc = lt & 1;
-                const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-                mbar_wait(tempty_bar(acc), aph ^ 1);
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + acc * Cfg::ACC_COLS;
-                bool first = true;
-                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                    mbar_wait(full_bar(s), ph);
-                    mbar_wait(ready_bar(s), ph);
+            int s = 0; uint32_t ph = 0; uint32_t g = 0;
+            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+                int c_begin;
+                const int nch = task_chunks(task, c_begin);
+                int ch = 0;
+                while (ch < nch) {
+                    const int seg_end = min(ch + SEG_STAGES, nch);
+                    const uint32_t b = g & 1u;
+                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                    bool first = true;
+                    for (; ch < seg_end; ++ch) {
+                        mbar_wait(full_bar(s), ph);
+                        mbar_wait(ready_bar(s), ph);
+                        tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
-                        const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
-                        const uint64_t b = make_desc(hch(s) + ks * 32, 16, 1024);
-                        umma_tf32(dcol, a_hi, b, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                        umma_tf32(dcol + KP, a_lo, b, idesc_h, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
+                            const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
+                            const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
+                            umma_tf32(dcol, a_hi, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                            umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                        }
+                        first = false;
+                        umma_commit(empty_bar(s));
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
-                    first = false;
-                    umma_commit(empty_bar(s));
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    umma_commit(tfull_bar(b));
+                    ++g;
                 }
-                umma_commit(tfull_bar(acc));
             }
         }
     } else if (warp < 6) {
         const int tid_s = threadIdx.x - 64;
         int s = 0; uint32_t ph = 0;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-            int c_begin, c_end;
-            task_cols(task, c_begin, c_end);
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            for (int ch = 0; ch < nch; ++ch) {
                 mbar_wait(full_bar(s), ph);
                 uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
                 split_buffer(reinterpret_cast<float4*>(stage), reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
@@ -456,29 +515,45 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         }
     } else {
         const int q = warp & 3;
-        int lt = 0;
-        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x, ++lt) {
-            const int acc = lt & 1;
-            const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-            mbar_wait(tfull_bar(acc), aph);
-            tc_fence_after();
-            const int row = (task % num_rb) * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
-#pragma unroll 1
-            for (int j0 = 0; j0 < KP; j0 += 16) {
-                float hi[16], lo[16];
-                tmem_ld16(taddr + j0, hi);
-                tmem_ld16(taddr + KP + j0, lo);
-                tmem_ld_wait();
-                if (row < d) {
-                    float* dst = P + (int64_t)row * KP + j0;
+        const int jbase = ((warp - 6) >> 2) * Cfg::NJ;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            const int nseg = (nch + SEG_STAGES - 1) / SEG_STAGES;
+            float areg[Cfg::NJ];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j, hi[j] + lo[j]);
+            for (int j = 0; j < Cfg::NJ; ++j) areg[j] = 0.f;
+            for (int seg = 0; seg < nseg; ++seg, ++g) {
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
+#pragma unroll
+                for (int j0 = 0; j0 < Cfg::NJ; j0 += 16) {
+                    float hi[16], sm[16];
+                    tmem_ld16(taddr + j0, hi);
+                    tmem_ld16(taddr + KP + j0, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) areg[j0 + j] += hi[j] + sm[j];
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            const int row = (task % num_rb) * 128 + q * 32 + lane;
+            if (dbg != nullptr && task == 0) {
+                float* o = dbg + (size_t)(q * 32 + lane) * KP + jbase;
+#pragma unroll
+                for (int j = 0; j < Cfg::NJ; ++j) o[j] = areg[j];
+            }
+            if (row < d) {
+                float* dst = P + (int64_t)row * KP + jbase;
+#pragma unroll
+                for (int j = 0; j < Cfg::NJ; ++j) atomicAdd(dst + j, areg[j]);
+            }
         }
     }
     tc_fence_before();
@@ -516,6 +591,7 @@ struct TcPlan {
     float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
     CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
     int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
+    float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
     std::string err;
 };
 
@@ -536,7 +612,7 @@ inline EncodeTiledFn get_encode_fn() {
 // 2-D fp32 row-major matrix (rows x cols, leading dimension ld), box = 32 columns x box_rows, 128B swizzle,
 // out-of-bounds elements read as zero.
 inline bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                     std::string* err) {
+                     bool mn_major, std::string* err) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -544,7 +620,8 @@ inline bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return false; }
     return true;
@@ -581,13 +658,13 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     if (cudaMalloc(&p.Wsplit, (size_t)d * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Wsplit failed"; return 1; }
     if (cudaMalloc(&p.Gsplit, (size_t)kp * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Gsplit failed"; return 1; }
     bool ok = true;
-    ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, &p.err);
-    ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, &p.err);
-    ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * kp, 2 * kp, tc::R1, &p.err);
-    ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, &p.err);
+    ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, true, &p.err);
+    ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, false, &p.err);
+    ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * kp, 2 * kp, tc::R1, true, &p.err);
+    ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, true, &p.err);
     for (int i = 0; i < 2; ++i) {
-        ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, &p.err);
-        ok = ok && make_map(&p.mapH_x[i], p.Hbuf[i], kp, n_loc, ldh, kp, &p.err);
+        ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
+        ok = ok && make_map(&p.mapH_x[i], p.Hbuf[i], kp, n_loc, ldh, kp, false, &p.err);
     }
     if (!ok) return 1;
     int rc = kp == 32 ? tc_set_attrs<32>() : kp == 64 ? tc_set_attrs<64>() : kp == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
@@ -618,8 +695,8 @@ inline int tc_after_gram(TcPlan& p, const DevState* st, const float* W, const fl
 template <int KP>
 inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = std::min(p.h_tiles, p.sm_count);
-    tc::k_h_update_tc<KP><<<grid, tc::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles);
+    tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
 }
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
@@ -636,8 +713,8 @@ inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn
 template <int KP>
 inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
     const int grid = std::min(p.x_tasks, p.sm_count);
-    tc::k_xht_tc<KP><<<grid, tc::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks);
+    tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks, p.dbg);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;

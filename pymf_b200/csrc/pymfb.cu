@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pymfb.h"
@@ -531,36 +532,89 @@ int pymfb_bind_x(pymfb_ctx* c, const float* x_dev, int64_t ld) {
     return data_changed(c);
 }
 
+// Host -> device ingest of X: a ring of pinned staging buffers is filled by a
+// few host threads (pageable user memory -> pinned) while the previous chunk's H2D copy (and the
+// fp64 -> fp32 cast kernel) run on the context's stream.
+static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
+    const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
+    const int64_t row_bytes = c->n_loc * (int64_t)esz;
+    const int NB = 3;
+    int64_t rows_per = std::max<int64_t>(1, (32LL << 20) / row_bytes);
+    rows_per = std::min(rows_per, c->d);
+    const size_t buf_bytes = (size_t)rows_per * row_bytes;
+    void* pinned[NB] = {nullptr, nullptr, nullptr};
+    void* dstage[NB] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(c->stream);
+        for (int b = 0; b < NB; ++b) {
+            if (pinned[b]) cudaFreeHost(pinned[b]);
+            if (dstage[b]) cudaFree(dstage[b]);
+            if (ev[b]) cudaEventDestroy(ev[b]);
+        }
+    };
+#define UP(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rc = fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+            cleanup();                                                                             \
+            return rc;                                                                             \
+        }                                                                                          \
+    } while (0)
+    for (int b = 0; b < NB; ++b) {
+        UP(cudaHostAlloc(&pinned[b], buf_bytes, cudaHostAllocDefault));
+        if (dtype == PYMFB_F64) UP(cudaMalloc(&dstage[b], buf_bytes));
+        UP(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthr = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+    int64_t chunk = 0;
+    for (int64_t r0 = 0; r0 < c->d; r0 += rows_per, ++chunk) {
+        const int b = (int)(chunk % NB);
+        const int64_t nr = std::min(rows_per, c->d - r0);
+        if (chunk >= NB) UP(cudaEventSynchronize(ev[b]));
+        {   // pageable -> pinned, rows split over threads
+            std::vector<std::thread> th;
+            const int64_t per = (nr + nthr - 1) / nthr;
+            for (int t = 0; t < nthr; ++t) {
+                const int64_t a = t * per, e = std::min(nr, a + per);
+                if (a >= e) break;
+                th.emplace_back([=]() {
+                    const char* src = (const char*)host + (size_t)(r0 + a) * ld * esz;
+                    char* dst = (char*)pinned[b] + (size_t)a * row_bytes;
+                    if (ld == c->n_loc) memcpy(dst, src, (size_t)(e - a) * row_bytes);
+                    else for (int64_t r = a; r < e; ++r, src += (size_t)ld * esz, dst += row_bytes) memcpy(dst, src, row_bytes);
+                });
+            }
+            for (auto& t : th) t.join();
+        }
+        if (dtype == PYMFB_F32) {
+            UP(cudaMemcpy2DAsync(c->X_own + r0 * c->ldx, c->ldx * sizeof(float), pinned[b], row_bytes, row_bytes, nr,
+                                 cudaMemcpyHostToDevice, c->stream));
+        } else {
+            UP(cudaMemcpyAsync(dstage[b], pinned[b], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, c->stream));
+            k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
+                (const double*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
+            c->launches += 1;
+            UP(cudaGetLastError());
+        }
+        UP(cudaEventRecord(ev[b], c->stream));
+    }
+#undef UP
+    cleanup();
+    return 0;
+}
+
 int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
     if (!c) return fail("null context");
     if (!x_host) return fail("x_host is null");
     if (ld < c->n_loc) return fail("leading dimension too small");
+    if (dtype != PYMFB_F32 && dtype != PYMFB_F64) return fail("bad dtype %d", dtype);
     CU(cudaSetDevice(c->device));
     CK(ensure_own_x(c));
-    if (dtype == PYMFB_F32) {
-        CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), x_host, ld * sizeof(float),
-                             c->n_loc * sizeof(float), c->d, cudaMemcpyHostToDevice, c->stream));
-    } else if (dtype == PYMFB_F64) {
-        // chunked: rows of fp64 -> device staging -> cast kernel
-        const int64_t max_chunk_bytes = 256LL << 20;
-        int64_t rows_per = std::max<int64_t>(1, max_chunk_bytes / (int64_t)(c->n_loc * sizeof(double)));
-        rows_per = std::min(rows_per, c->d);
-        double* stage = nullptr;
-        CU(cudaMalloc(&stage, (size_t)rows_per * c->n_loc * sizeof(double)));
-        for (int64_t r0 = 0; r0 < c->d; r0 += rows_per) {
-            int64_t nr = std::min(rows_per, c->d - r0);
-            CU(cudaMemcpy2DAsync(stage, c->n_loc * sizeof(double), (const double*)x_host + r0 * ld, ld * sizeof(double),
-                                 c->n_loc * sizeof(double), nr, cudaMemcpyHostToDevice, c->stream));
-            k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-                stage, c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
-            c->launches += 1;
-            CU(cudaGetLastError());
-        }
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaFree(stage));
-    } else {
-        return fail("bad dtype %d", dtype);
-    }
+    CK(staged_upload(c, x_host, dtype, ld));
     CU(cudaStreamSynchronize(c->stream));
     return data_changed(c);
 }

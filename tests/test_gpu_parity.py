@@ -141,7 +141,8 @@ def test_early_stop_state_is_consistent():
         Wr, Hr = W0.copy(), H0.copy()
         O.factorize(A, Wr, Hr, niter=done, early_stop=False)
         assert rel(W, Wr) < 5e-3 and rel(H, Hr) < 5e-3     # long run (thousand+ iterations)
-        assert abs(O.frobenius_norm(A, W, H) - ferr[-1]) / ferr[-1] < TOL_FERR
+        # near-exact fit: ferr ~ 1e-4 on ||A|| ~ 18, so allow the fp32 representation floor of W/H
+        assert abs(O.frobenius_norm(A, W, H) - ferr[-1]) < TOL_FERR * ferr[-1] + 1e-6 * np.linalg.norm(A)
         # a second run continues from that state (warm start) and does not crash
         f2, d2 = e.run(3, early_stop=True)
         assert d2 == 3 and len(f2) == 3
