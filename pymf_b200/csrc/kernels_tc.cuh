@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -74,6 +75,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) __trap();
     }
+}
+// One elected lane of a CONVERGED warp.  The producer and MMA warps run their loops with all 32 lanes
+// (warp-uniform control flow lets the compiler keep descriptors / addresses in uniform registers; a
+// lane-0-only branch made every tcgen05.mma cost ~90 issue cycles) and elect one lane per issue.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -240,28 +249,31 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        {
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int col0 = tile * TILE_COLS;
                 for (int it = 0; it < nit; ++it) {
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::WSTAGE_BYTES);
-                    const bool xphase = it < nd;
-                    const int r0 = (xphase ? it : it - nd) * R1;
-                    const CUtensorMap* ma = xphase ? &mapX : &mapH;
-                    const CUtensorMap* mb = xphase ? &mapW : &mapG;
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::WSTAGE_BYTES);
+                        const bool xphase = it < nd;
+                        const int r0 = (xphase ? it : it - nd) * R1;
+                        const CUtensorMap* ma = xphase ? &mapX : &mapH;
+                        const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) tma_load_2d(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0);
+                        for (int c = 0; c < 4; ++c) tma_load_2d(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0);
 #pragma unroll
-                    for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+                    }
+                    __syncwarp();
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 1, 1);
             int s = 0; uint32_t ph = 0; uint32_t g = 0;
@@ -278,20 +290,24 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         mbar_wait(full_bar(s), ph);
                         mbar_wait(ready_bar(s), ph);
                         tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kg = 0; kg < R1 / 8; ++kg) {
-                            // one MMA (K = 8) = two 4-row swizzle atoms (SBO = 512 B); 32-column chunks LBO apart
-                            const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 512, 1);
-                            const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 512, 1);
-                            const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
-                            umma_tf32(dcol, a_hi, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
-                            umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                            for (int kg = 0; kg < R1 / 8; ++kg) {
+                                // one MMA (K = 8) = two 4-row swizzle atoms (SBO = 512 B); 32-column chunks LBO apart
+                                const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 512, 1);
+                                const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 512, 1);
+                                const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
+                                umma_tf32(dcol, a_hi, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                                umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                            }
+                            umma_commit(empty_bar(s));
                         }
+                        __syncwarp();
                         first = false;
-                        umma_commit(empty_bar(s));
                         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(tfull_bar(b));
+                    if (elect_one()) umma_commit(tfull_bar(b));
+                    __syncwarp();
                     ++g;
                 }
             }
@@ -442,7 +458,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int s = 0; uint32_t ph = 0;
             for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
                 int c_begin;
@@ -450,15 +466,18 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const int row0 = (task % num_rb) * 128;
                 for (int ch = 0; ch < nch; ++ch) {
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
-                    tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
-                    tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
+                        tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
+                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
+                    }
+                    __syncwarp();
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
             int s = 0; uint32_t ph = 0; uint32_t g = 0;
@@ -477,19 +496,23 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                         mbar_wait(full_bar(s), ph);
                         mbar_wait(ready_bar(s), ph);
                         tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
-                            const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
-                            const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
-                            umma_tf32(dcol, a_hi, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                            umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
+                                const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
+                                const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
+                                umma_tf32(dcol, a_hi, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                                umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                            }
+                            umma_commit(empty_bar(s));
                         }
+                        __syncwarp();
                         first = false;
-                        umma_commit(empty_bar(s));
                         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(tfull_bar(b));
+                    if (elect_one()) umma_commit(tfull_bar(b));
+                    __syncwarp();
                     ++g;
                 }
             }
@@ -561,6 +584,445 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================
+// TS variants (k <= 64): the X operand is fed to the tensor core from TENSOR MEMORY.
+//
+// With both operands in shared memory every byte of X crosses the 128 B/clk shared-memory port
+// ~7 times per pass (TMA write, split read, hi/lo writes, two MMA operand reads) and the pass is
+// shared-memory-bound at ~70 % of HBM speed (measured).  Here the 4 convert warps read each X
+// element from shared memory ONCE, split it in registers and park hi/lo in TMEM with tcgen05.st;
+// tcgen05.mma then takes A from TMEM and only the small [W_hi|W_lo] / [H_hi|H_lo] operand from
+// shared memory: ~3 B of shared-memory traffic per byte of X.
+//   TMEM columns: [0, 4KP) two segment accumulators, then NT x 64 columns of A ring (32 hi + 32 lo).
+// =============================================================================================
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int KP>
+struct TsCfg {
+    static constexpr int NCH = 2 * KP / 32;
+    static constexpr int BSTAGE_BYTES = NCH * R1 * 128;             // [b_hi | b_lo] operand per stage (= 2*KP*128)
+    static constexpr int STAGE_BYTES = XSTAGE_BYTES + BSTAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SEG_COLS = 2 * KP;
+    static constexpr int A_COL0 = 4 * KP;                           // first TMEM column of the A ring
+    static constexpr int NT_RAW = (512 - A_COL0) / 64;
+    static constexpr int NT = NT_RAW > 6 ? 6 : NT_RAW;
+    static constexpr int EPI_WARPS = 4;
+    static constexpr int NJ = KP;
+    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
+    static constexpr int NBAR = 2 * STAGES + 2 * NT + 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+    static_assert(KP == 32 || KP == 64, "TS kernels serve KP = 32 and 64");
+    static_assert(NT >= 2, "need at least two A buffers");
+    static_assert(NBAR * 8 + 8 <= 512, "barrier area too small");
+};
+
+// hi/lo of 32 values -> TMEM A ring slot (this thread's lane, 32 hi columns then 32 lo columns)
+__device__ __forceinline__ void park_hilo(uint32_t taddr, const float (&v)[32]) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+    }
+    tmem_st32(taddr, hi);
+    tmem_st32(taddr + 32, lo);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
+k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+              const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
+              const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
+              int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
+    using Cfg = TsCfg<KP>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto afull_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + t); };
+    auto aempty_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NT + t); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * Cfg::NBAR;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int t = 0; t < Cfg::NT; ++t) { mbar_init(afull_bar(t), 4); mbar_init(aempty_bar(t), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int nd = (d + R1 - 1) / R1;
+    const int nit = nd + KP / R1;
+    auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                    // [32 rows][128 cols] plain
+    auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };        // MN-major chunks
+
+    if (warp == 0) {
+        {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int col0 = tile * TILE_COLS;
+                for (int it = 0; it < nit; ++it) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::BSTAGE_BYTES);
+                        const bool xphase = it < nd;
+                        const int r0 = (xphase ? it : it - nd) * R1;
+                        tma_load_2d(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0);
+                        const CUtensorMap* mb = xphase ? &mapW : &mapG;
+#pragma unroll
+                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+                    }
+                    __syncwarp();
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {
+            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
+            constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
+            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int it = 0;
+                while (it < nit) {
+                    const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
+                    const uint32_t b = g & 1u;
+                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                    bool first = true;
+                    for (; it < seg_end; ++it) {
+                        mbar_wait(full_bar(s), ph);
+                        mbar_wait(afull_bar(t), tph);
+                        tc_fence_after();
+                        const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kg = 0; kg < R1 / 8; ++kg) {
+                                const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
+                                umma_tf32_ts(dcol, a_hi + kg * 8, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                                umma_tf32_ts(dcol + KP, a_hi + 32 + kg * 8, bd, idesc_h, 1u);
+                            }
+                            umma_commit(empty_bar(s));
+                            umma_commit(aempty_bar(t));
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                        if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(tfull_bar(b));
+                    __syncwarp();
+                    ++g;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
+        const int q = warp & 3;
+        const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
+        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; it < nit; ++it) {
+                mbar_wait(full_bar(s), ph);
+                mbar_wait(aempty_bar(t), tph ^ 1);
+                tc_fence_after();
+                const float* xs = reinterpret_cast<const float*>(smem_gen + s * Cfg::STAGE_BYTES);
+                float v[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = xs[r * TILE_COLS + mylane];
+                park_hilo(lane_addr + t * 64, v);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull_bar(t));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            float creg[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) creg[j] = 0.f;
+            for (int seg = 0; seg < nsegC; ++seg, ++g) {
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+                    float hi[16], sm[16];
+                    tmem_ld16(taddr + j0, hi);
+                    tmem_ld16(taddr + KP + j0, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+            }
+            {
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+                const int col = tile * TILE_COLS + q * 32 + lane;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+                    float dh[16], dl[16];
+                    tmem_ld16(taddr + j0, dh);
+                    tmem_ld16(taddr + KP + j0, dl);
+                    tmem_ld_wait();
+                    if (dbg != nullptr && tile == 0) {
+                        float* o = dbg + (size_t)(q * 32 + lane) * (2 * KP) + j0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { o[j] = creg[j0 + j]; o[KP + j] = dh[j] + dl[j]; }
+                    }
+                    if (col < n_loc) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int64_t o = (int64_t)(j0 + j) * ldh + col;
+                            const float h = Hc[o];
+                            Hn[o] = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+                ++g;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
+k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
+         const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
+         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg) {
+    using Cfg = TsCfg<KP>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto afull_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + t); };
+    auto aempty_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NT + t); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * Cfg::NBAR;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapH);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int t = 0; t < Cfg::NT; ++t) { mbar_init(afull_bar(t), 4); mbar_init(aempty_bar(t), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                  // [128 rows][128 B] SW128
+    auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };      // [2KP rows][128 B] SW128
+    auto task_chunks = [&](int task, int& c_begin) {
+        const int cs = task / num_rb;
+        c_begin = cs * cols_per_task;
+        const int c_end = min(n_loc, c_begin + cols_per_task);
+        return (c_end - c_begin + 31) / 32;
+    };
+
+    if (warp == 0) {
+        {
+            int s = 0; uint32_t ph = 0;
+            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+                int c_begin;
+                const int nch = task_chunks(task, c_begin);
+                const int row0 = (task % num_rb) * 128;
+                for (int ch = 0; ch < nch; ++ch) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
+                        tma_load_2d(xs_addr(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
+                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
+                    }
+                    __syncwarp();
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {
+            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
+            constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
+            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
+            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+                int c_begin;
+                const int nch = task_chunks(task, c_begin);
+                int ch = 0;
+                while (ch < nch) {
+                    const int seg_end = min(ch + SEG_STAGES, nch);
+                    const uint32_t b = g & 1u;
+                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                    bool first = true;
+                    for (; ch < seg_end; ++ch) {
+                        mbar_wait(full_bar(s), ph);
+                        mbar_wait(afull_bar(t), tph);
+                        tc_fence_after();
+                        const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
+                                umma_tf32_ts(dcol, a_hi + ks * 8, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                                umma_tf32_ts(dcol + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
+                            }
+                            umma_commit(empty_bar(s));
+                            umma_commit(aempty_bar(t));
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                        if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(tfull_bar(b));
+                    __syncwarp();
+                    ++g;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // convert warps: thread <-> row of the X block (TMEM lane); reads its 128 B row (SW128: 16 B
+        // chunk j sits at (j ^ (row & 7))), parks hi/lo in TMEM; also splits the H chunk in shared memory.
+        const int q = warp & 3;
+        const int myrow = q * 32 + lane;
+        const int tid_s = threadIdx.x - 64;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
+        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            for (int ch = 0; ch < nch; ++ch) {
+                mbar_wait(full_bar(s), ph);
+                mbar_wait(aempty_bar(t), tph ^ 1);
+                tc_fence_after();
+                uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
+                const uint8_t* rowp = stage + myrow * 128;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 f = *reinterpret_cast<const float4*>(rowp + ((j ^ (myrow & 7)) << 4));
+                    v[4 * j + 0] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+                }
+                park_hilo(lane_addr + t * 64, v);
+                split_buffer(reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
+                             reinterpret_cast<float4*>(stage + XSTAGE_BYTES + KP * 128), KP * 128 / 16, tid_s, 128);
+                fence_proxy_async();
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull_bar(t));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            const int nseg = (nch + SEG_STAGES - 1) / SEG_STAGES;
+            float areg[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) areg[j] = 0.f;
+            for (int seg = 0; seg < nseg; ++seg, ++g) {
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+                    float hi[16], sm[16];
+                    tmem_ld16(taddr + j0, hi);
+                    tmem_ld16(taddr + KP + j0, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) areg[j0 + j] += hi[j] + sm[j];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+            }
+            const int row = (task % num_rb) * 128 + q * 32 + lane;
+            if (dbg != nullptr && task == 0) {
+                float* o = dbg + (size_t)(q * 32 + lane) * KP;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) o[j] = areg[j];
+            }
+            if (row < d) {
+                float* dst = P + (int64_t)row * KP;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) atomicAdd(dst + j, areg[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // [hi | lo] split of a small row-major matrix: src rows x kp -> dst rows x 2kp   (W and G)
 __global__ void k_split_hilo(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int kp,
                              float* __restrict__ dst) {
@@ -590,6 +1052,8 @@ struct TcPlan {
     float* Wsplit = nullptr;   // d x 2kp  [W_hi | W_lo]
     float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
     CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
+    CUtensorMap mapX_p, mapH_p[2];   // TS kernels: plain (unswizzled) 128-column x 32-row boxes
+    bool use_ts = false;             // k <= 64: A operand from TMEM (k_*_ts), else both operands in smem
     int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
     std::string err;
@@ -627,12 +1091,36 @@ inline bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
     return true;
 }
 
+// plain (unswizzled) map: box = box_cols x box_rows
+inline bool make_map_plain(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                           int box_rows, std::string* err) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled(plain) failed with code " + std::to_string((int)r); return false; }
+    return true;
+}
+
 inline bool tc_supported(int64_t d, int64_t n_loc, int kp, int64_t ldx, const float* X, std::string* why) {
     if (kp % 32 != 0 || kp < 32 || kp > 128) { *why = "k (padded) must be 32..128 in steps of 32"; return false; }
     if (ldx % 4 != 0 || ((uintptr_t)X & 15) != 0) { *why = "X must be 16-byte aligned with ld % 4 == 0"; return false; }
     if (d >= (1LL << 31) || n_loc >= (1LL << 31) - 256) { *why = "dimension too large"; return false; }
     if (d < 64 || n_loc < 128) { *why = "problem too small for the tensor-core tiles"; return false; }
     return true;
+}
+
+template <int KP>
+inline int ts_set_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(tc::k_h_update_ts<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsCfg<KP>::SMEM_BYTES);
+    if (e != cudaSuccess) return 1;
+    e = cudaFuncSetAttribute(tc::k_xht_ts<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsCfg<KP>::SMEM_BYTES);
+    return e == cudaSuccess ? 0 : 1;
 }
 
 template <int KP>
@@ -666,7 +1154,14 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
         ok = ok && make_map(&p.mapH_x[i], p.Hbuf[i], kp, n_loc, ldh, kp, false, &p.err);
     }
+    ok = ok && make_map_plain(&p.mapX_p, X, d, n_loc, ldx, tc::TILE_COLS, tc::R1, &p.err);
+    for (int i = 0; i < 2; ++i) ok = ok && make_map_plain(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, tc::TILE_COLS, tc::R1, &p.err);
     if (!ok) return 1;
+    {
+        const char* force_ss = getenv("PYMFB_TC_FORCE_SS");
+        p.use_ts = kp <= 64 && !(force_ss && force_ss[0] == '1');
+        if (p.use_ts && (kp == 32 ? ts_set_attrs<32>() : ts_set_attrs<64>())) { p.err = "cudaFuncSetAttribute (TS kernels) failed"; return 1; }
+    }
     int rc = kp == 32 ? tc_set_attrs<32>() : kp == 64 ? tc_set_attrs<64>() : kp == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
     if (rc) { p.err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; return 1; }
     p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
@@ -698,8 +1193,25 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
     tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
 }
+template <int KP>
+inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
+    const int grid = std::min(p.h_tiles, p.sm_count);
+    tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
+}
+template <int KP>
+inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
+    const int grid = std::min(p.x_tasks, p.sm_count);
+    tc::k_xht_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks, p.dbg);
+}
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    if (p.use_ts) {
+        if (p.kp == 32) ts_launch_h<32>(p, st, hsrc, Hn, stream); else ts_launch_h<64>(p, st, hsrc, Hn, stream);
+        *launches += 1;
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     switch (p.kp) {
         case 32: tc_launch_h<32>(p, st, hsrc, Hn, stream); break;
         case 64: tc_launch_h<64>(p, st, hsrc, Hn, stream); break;
@@ -718,6 +1230,11 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    if (p.use_ts) {
+        if (p.kp == 32) ts_launch_x<32>(p, st, hsrc, P, stream); else ts_launch_x<64>(p, st, hsrc, P, stream);
+        *launches += 1;
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     switch (p.kp) {
         case 32: tc_launch_x<32>(p, st, hsrc, P, stream); break;
         case 64: tc_launch_x<64>(p, st, hsrc, P, stream); break;
