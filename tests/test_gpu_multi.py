@@ -1,0 +1,68 @@
+"""Two-rank NCCL run of the column-sharded path against the single-GPU result and the oracle.
+Needs >= 2 B200s: run with `-m gpu` on a multi-GPU box (skipped when fewer are visible)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import pymf_b200
+from oracle import nmf_oracle as O
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+d, n, k, niter = %(d)d, %(n)d, %(k)d, %(niter)d
+X = O.gen_matrix(21, d, n)
+bounds = [int(round(n * r / float(world))) for r in range(world + 1)]
+lo, hi = bounds[rank], bounds[rank + 1]
+np.random.seed(5)
+m = pymf_b200.NMF(np.ascontiguousarray(X[:, lo:hi]), num_bases=k, process_group=True, device=rank, path=%(path)r)
+m.factorize(niter=niter)
+np.savez(os.path.join(%(out)r, "r%%d.npz" %% rank), W=m.W, H=m.H, ferr=m.ferr, lo=lo, hi=hi)
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("shape,path", [((512, 1000, 32), "tc"), ((300, 777, 10), "simt"), ((1024, 4096, 128), "tc")])
+def test_two_gpus_match_oracle(tmp_path, shape, path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d, n, k = shape
+    niter = 6
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT, d=d, n=n, k=k, niter=niter, out=str(tmp_path), path=path))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    from oracle import nmf_oracle as O
+    X = O.gen_matrix(21, d, n).astype(np.float64)
+    np.random.seed(5)
+    W, H = O.init_wh(d, n, k)
+    ferr = O.factorize(X, W, H, niter=niter)
+    parts = [np.load(str(tmp_path / ("r%d.npz" % r_))) for r_ in range(2)]
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+    for p in parts:
+        assert rel(p["W"], W) < 1e-4
+        assert rel(p["H"], H[:, int(p["lo"]):int(p["hi"])]) < 1e-4
+        assert np.max(np.abs(p["ferr"] - ferr) / ferr) < 1e-3
+    np.testing.assert_array_equal(parts[0]["W"], parts[1]["W"])      # replicas stay bit-identical
+    np.testing.assert_array_equal(parts[0]["ferr"], parts[1]["ferr"])
