@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(HCfg<KP>::THREADS, 1)
 k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
-              int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
+              float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
     using Cfg = HCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -379,7 +379,11 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(jbase + j0 + j) * ldh + col;
                             const float h = Hc[o];
-                            Hn[o] = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                            const float hn = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                            const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
+                            Hn[o] = hn;                                  // new H
+                            Hs[o] = hh;                                  // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[o + (int64_t)KP * ldh] = hn - hh;
                         }
                     }
                 }
@@ -467,9 +471,9 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 for (int ch = 0; ch < nch; ++ch) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
                         tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
-                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
+                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);   // [H_hi ; H_lo] rows
                     }
                     __syncwarp();
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -528,8 +532,6 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
                 split_buffer(reinterpret_cast<float4*>(stage), reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
                              XSTAGE_BYTES / 16, tid_s, 128);
-                split_buffer(reinterpret_cast<float4*>(stage + 2 * XSTAGE_BYTES),
-                             reinterpret_cast<float4*>(stage + 2 * XSTAGE_BYTES + KP * 128), KP * 128 / 16, tid_s, 128);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ready_bar(s));
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
 k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
-              int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
+              float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -821,7 +823,11 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
                             const float h = Hc[o];
-                            Hn[o] = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                            const float hn = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
+                            const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
+                            Hn[o] = hn;                                  // new H
+                            Hs[o] = hh;                                  // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[o + (int64_t)KP * ldh] = hn - hh;
                         }
                     }
                 }
@@ -837,11 +843,21 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+constexpr int X_CONV_GROUPS = 2;                          // convert-warp groups of the X.H^T pass (alternate stages)
+constexpr int X_THREADS = 32 * (2 + 4 * X_CONV_GROUPS + 4);
+
+// X H^T pass, TS variant.  Tasks [0, x_tasks): (128-row block of X, column range) -> P_A += X H^T.
+// Tasks [x_tasks, num_tasks): column ranges of H itself as the A operand -> P_B += H H^T (same code,
+// rows >= k are zero-filled by TMA).  B operand = [H_hi ; H_lo] rows, pre-split by the H-update
+// epilogue (or k_split_rows), so the convert warps only touch X.  Two groups of 4 convert warps take
+// alternate stages (the single group was ~75 % busy and the critical path of this pass).
 template <int KP>
-__global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
-k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
-         const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
-         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg) {
+__global__ void __launch_bounds__(X_THREADS, 1)
+k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapHs,
+         const __grid_constant__ CUtensorMap mapHA, const DevState* __restrict__ st,
+         float* __restrict__ PA, float* __restrict__ PB, int d, int n_loc,
+         int cols_per_task, int num_rb, int x_tasks, int hh_cols_per_task, int num_tasks,
+         float* __restrict__ dbg) {
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -858,11 +874,12 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EPI_WARP0 = 2 + 4 * X_CONV_GROUPS;
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapH);
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapHs); tma_prefetch_desc(&mapHA);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int t = 0; t < Cfg::NT; ++t) { mbar_init(afull_bar(t), 4); mbar_init(aempty_bar(t), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -873,91 +890,93 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 
     auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                  // [128 rows][128 B] SW128
     auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };      // [2KP rows][128 B] SW128
-    auto task_chunks = [&](int task, int& c_begin) {
-        const int cs = task / num_rb;
-        c_begin = cs * cols_per_task;
-        const int c_end = min(n_loc, c_begin + cols_per_task);
+    // task -> (first column, number of 32-column stages, first row, is H H^T task)
+    auto task_info = [&](int task, int& c_begin, int& row0, bool& hh) {
+        hh = task >= x_tasks;
+        int cpt, cs;
+        if (hh) { cs = task - x_tasks; cpt = hh_cols_per_task; row0 = 0; }
+        else { cs = task / num_rb; cpt = cols_per_task; row0 = (task % num_rb) * 128; }
+        c_begin = cs * cpt;
+        const int c_end = min(n_loc, c_begin + cpt);
         return (c_end - c_begin + 31) / 32;
     };
 
     if (warp == 0) {
-        {
-            int s = 0; uint32_t ph = 0;
-            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-                int c_begin;
-                const int nch = task_chunks(task, c_begin);
-                const int row0 = (task % num_rb) * 128;
-                for (int ch = 0; ch < nch; ++ch) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + KP * 128);
-                        tma_load_2d(xs_addr(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
-                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);
-                    }
-                    __syncwarp();
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        int s = 0; uint32_t ph = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin, row0; bool hh;
+            const int nch = task_info(task, c_begin, row0, hh);
+            const CUtensorMap* ma = hh ? &mapHA : &mapX;
+            for (int ch = 0; ch < nch; ++ch) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
+                    tma_load_2d(xs_addr(s), ma, full_bar(s), c_begin + 32 * ch, row0);
+                    tma_load_2d(hch(s), &mapHs, full_bar(s), c_begin + 32 * ch, 0);
                 }
+                __syncwarp();
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        {
-            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
-            constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
-            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
-            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-                int c_begin;
-                const int nch = task_chunks(task, c_begin);
-                int ch = 0;
-                while (ch < nch) {
-                    const int seg_end = min(ch + SEG_STAGES, nch);
-                    const uint32_t b = g & 1u;
-                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+        constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
+        constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
+        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin, row0; bool hh;
+            const int nch = task_info(task, c_begin, row0, hh);
+            int ch = 0;
+            while (ch < nch) {
+                const int seg_end = min(ch + SEG_STAGES, nch);
+                const uint32_t b = g & 1u;
+                mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                bool first = true;
+                for (; ch < seg_end; ++ch) {
+                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(afull_bar(t), tph);
                     tc_fence_after();
-                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
-                    bool first = true;
-                    for (; ch < seg_end; ++ch) {
-                        mbar_wait(full_bar(s), ph);
-                        mbar_wait(afull_bar(t), tph);
-                        tc_fence_after();
-                        const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
-                        if (elect_one()) {
+                    const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
+                    if (elect_one()) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
-                                umma_tf32_ts(dcol, a_hi + ks * 8, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                                umma_tf32_ts(dcol + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
-                            }
-                            umma_commit(empty_bar(s));
-                            umma_commit(aempty_bar(t));
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
+                            umma_tf32_ts(dcol, a_hi + ks * 8, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                            umma_tf32_ts(dcol + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
                         }
-                        __syncwarp();
-                        first = false;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
-                        if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                        umma_commit(empty_bar(s));
+                        umma_commit(aempty_bar(t));
                     }
-                    if (elect_one()) umma_commit(tfull_bar(b));
                     __syncwarp();
-                    ++g;
+                    first = false;
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    if (++t == Cfg::NT) { t = 0; tph ^= 1; }
                 }
+                if (elect_one()) umma_commit(tfull_bar(b));
+                __syncwarp();
+                ++g;
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < EPI_WARP0) {
         // convert warps: thread <-> row of the X block (TMEM lane); reads its 128 B row (SW128: 16 B
-        // chunk j sits at (j ^ (row & 7))), parks hi/lo in TMEM; also splits the H chunk in shared memory.
+        // chunk j sits at (j ^ (row & 7))), splits in registers, parks hi/lo in the TMEM A ring.
         const int q = warp & 3;
+        const int group = (warp - 2) >> 2;
         const int myrow = q * 32 + lane;
-        const int tid_s = threadIdx.x - 64;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
-        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0;
+        uint32_t c = 0;                                     // stage counter of this CTA
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-            int c_begin;
-            const int nch = task_chunks(task, c_begin);
-            for (int ch = 0; ch < nch; ++ch) {
+            int c_begin, row0; bool hh;
+            const int nch = task_info(task, c_begin, row0, hh);
+            for (int ch = 0; ch < nch; ++ch, ++c) {
+                if ((int)(c % X_CONV_GROUPS) != group) continue;
+                const int s = (int)(c % Cfg::STAGES), t = (int)(c % Cfg::NT);
+                const uint32_t ph = (c / Cfg::STAGES) & 1u, tph = (c / Cfg::NT) & 1u;
                 mbar_wait(full_bar(s), ph);
                 mbar_wait(aempty_bar(t), tph ^ 1);
                 tc_fence_after();
-                uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
-                const uint8_t* rowp = stage + myrow * 128;
+                const uint8_t* rowp = smem_gen + s * Cfg::STAGE_BYTES + myrow * 128;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -965,15 +984,10 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     v[4 * j + 0] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
                 }
                 park_hilo(lane_addr + t * 64, v);
-                split_buffer(reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
-                             reinterpret_cast<float4*>(stage + XSTAGE_BYTES + KP * 128), KP * 128 / 16, tid_s, 128);
-                fence_proxy_async();
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull_bar(t));
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
-                if (++t == Cfg::NT) { t = 0; tph ^= 1; }
             }
         }
     } else {
@@ -981,8 +995,8 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-            int c_begin;
-            const int nch = task_chunks(task, c_begin);
+            int c_begin, row0; bool hh;
+            const int nch = task_info(task, c_begin, row0, hh);
             const int nseg = (nch + SEG_STAGES - 1) / SEG_STAGES;
             float areg[KP];
 #pragma unroll
@@ -1005,14 +1019,14 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(b));
             }
-            const int row = (task % num_rb) * 128 + q * 32 + lane;
+            const int row = row0 + q * 32 + lane;
             if (dbg != nullptr && task == 0) {
                 float* o = dbg + (size_t)(q * 32 + lane) * KP;
 #pragma unroll
                 for (int j = 0; j < KP; ++j) o[j] = areg[j];
             }
-            if (row < d) {
-                float* dst = P + (int64_t)row * KP;
+            if (row < (hh ? KP : d)) {
+                float* dst = (hh ? PB : PA) + (int64_t)row * KP;
 #pragma unroll
                 for (int j = 0; j < KP; ++j) atomicAdd(dst + j, areg[j]);
             }
@@ -1021,6 +1035,20 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// H (kp x ldh) -> Hs = [H_hi rows ; H_lo rows] (2kp x ldh); used when the X.H^T pass runs on an H that
+// did not come out of the H-update epilogue (bootstrap, user-assigned H).
+__global__ void k_split_rows(const DevState* __restrict__ st, const float* __restrict__ H, int kp, int64_t ldh,
+                             float* __restrict__ Hs) {
+    if (st->stop) return;
+    const int64_t total = (int64_t)kp * ldh;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = H[i];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        Hs[i] = hi;
+        Hs[i + total] = v - hi;
+    }
 }
 
 // [hi | lo] split of a small row-major matrix: src rows x kp -> dst rows x 2kp   (W and G)
@@ -1049,10 +1077,14 @@ struct TcPlan {
     int k = 0, kp = 0;
     const float* X = nullptr;
     const float* Hbuf[2] = {nullptr, nullptr};
+    float* Hs[2] = {nullptr, nullptr};        // [H_hi ; H_lo] (2kp x ldh) companion of each H buffer
+    bool hs_valid[2] = {false, false};
     float* Wsplit = nullptr;   // d x 2kp  [W_hi | W_lo]
     float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
     CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
     CUtensorMap mapX_p, mapH_p[2];   // TS kernels: plain (unswizzled) 128-column x 32-row boxes
+    CUtensorMap mapH_a[2];           // H as the A operand of the H.H^T tasks (128-row boxes, rows >= kp zero-filled)
+    int hh_tasks = 0, hh_cols_per_task = 0;
     bool use_ts = false;             // k <= 64: A operand from TMEM (k_*_ts), else both operands in smem
     int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
@@ -1134,6 +1166,7 @@ inline int tc_set_attrs() {
 inline void tc_release(TcPlan& p) {
     if (p.Wsplit) cudaFree(p.Wsplit);
     if (p.Gsplit) cudaFree(p.Gsplit);
+    for (int i = 0; i < 2; ++i) { if (p.Hs[i]) cudaFree(p.Hs[i]); p.Hs[i] = nullptr; p.hs_valid[i] = false; }
     p.Wsplit = p.Gsplit = nullptr;
     p.ready = false;
 }
@@ -1145,6 +1178,11 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     p.Hbuf[0] = H0; p.Hbuf[1] = H1;
     if (cudaMalloc(&p.Wsplit, (size_t)d * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Wsplit failed"; return 1; }
     if (cudaMalloc(&p.Gsplit, (size_t)kp * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Gsplit failed"; return 1; }
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc(&p.Hs[i], (size_t)2 * kp * ldh * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Hs failed"; return 1; }
+        cudaMemset(p.Hs[i], 0, (size_t)2 * kp * ldh * sizeof(float));
+        p.hs_valid[i] = false;
+    }
     bool ok = true;
     ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, true, &p.err);
     ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, false, &p.err);
@@ -1152,7 +1190,8 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, true, &p.err);
     for (int i = 0; i < 2; ++i) {
         ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
-        ok = ok && make_map(&p.mapH_x[i], p.Hbuf[i], kp, n_loc, ldh, kp, false, &p.err);
+        ok = ok && make_map(&p.mapH_x[i], p.Hs[i], 2 * kp, n_loc, ldh, 2 * kp, false, &p.err);   // [H_hi ; H_lo] as B
+        ok = ok && make_map(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 128, false, &p.err);        // H as A
     }
     ok = ok && make_map_plain(&p.mapX_p, X, d, n_loc, ldx, tc::TILE_COLS, tc::R1, &p.err);
     for (int i = 0; i < 2; ++i) ok = ok && make_map_plain(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, tc::TILE_COLS, tc::R1, &p.err);
@@ -1174,6 +1213,12 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     p.x_cols_per_task = (int)(chunks_per * 32);
     splits = (chunks + chunks_per - 1) / chunks_per;
     p.x_tasks = (int)(splits * p.x_rb);
+    {   // H H^T tasks (TS kernels): ~one short task per SM
+        int64_t hsplits = std::min<int64_t>(chunks, sm_count);
+        const int64_t hper = (chunks + hsplits - 1) / hsplits;
+        p.hh_cols_per_task = (int)(hper * 32);
+        p.hh_tasks = (int)((chunks + hper - 1) / hper);
+    }
     p.ready = true;
     return 0;
 }
@@ -1191,22 +1236,25 @@ template <int KP>
 inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = std::min(p.h_tiles, p.sm_count);
     tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
+        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
 }
 template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = std::min(p.h_tiles, p.sm_count);
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
+        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
 }
 template <int KP>
 inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
-    const int grid = std::min(p.x_tasks, p.sm_count);
-    tc::k_xht_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks, p.dbg);
+    const int ntasks = p.x_tasks + p.hh_tasks;
+    const int grid = std::min(ntasks, p.sm_count);
+    tc::k_xht_ts<KP><<<grid, tc::X_THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
+        p.mapX_x, p.mapH_x[hsrc], p.mapH_a[hsrc], st, P, P + p.d * p.kp, (int)p.d, (int)p.n_loc, p.x_cols_per_task,
+        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg);
 }
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    p.hs_valid[hsrc ^ 1] = true;    // the epilogue writes [H_hi ; H_lo] of the new H
     if (p.use_ts) {
         if (p.kp == 32) ts_launch_h<32>(p, st, hsrc, Hn, stream); else ts_launch_h<64>(p, st, hsrc, Hn, stream);
         *launches += 1;
@@ -1228,8 +1276,15 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks, p.dbg);
 }
+// true when the launch also produced H H^T (so the caller skips its own H H^T kernel)
+inline bool tc_xht_includes_hht(const TcPlan& p) { return p.use_ts; }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
+    if (!p.hs_valid[hsrc]) {
+        tc::k_split_rows<<<4 * p.sm_count, 256, 0, stream>>>(st, Hc, p.kp, p.ldh, p.Hs[hsrc]);
+        *launches += 1;
+        p.hs_valid[hsrc] = true;
+    }
     if (p.use_ts) {
         if (p.kp == 32) ts_launch_x<32>(p, st, hsrc, P, stream); else ts_launch_x<64>(p, st, hsrc, P, stream);
         *launches += 1;

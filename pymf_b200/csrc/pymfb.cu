@@ -280,7 +280,7 @@ static int launch_xht(pymfb_ctx* c) {
         CU(cudaGetLastError());
     }
     CK(timing_end(c, 1, e0, e1));
-    {   // B = H H^T  (X := H)
+    if (!(c->path == PYMFB_PATH_TC && tc_xht_includes_hht(c->tc))) {   // B = H H^T  (X := H)
         int64_t cps; unsigned ns;
         xht_splits(c, c->kp, &cps, &ns);
         dim3 grid((unsigned)((c->kp + 127) / 128), ns, (unsigned)(c->kp / c->kb));
@@ -677,7 +677,7 @@ int pymfb_set_w(pymfb_ctx* c, const void* w_host, int dtype) {
 int pymfb_set_h(pymfb_ctx* c, const void* h_host, int dtype) {
     if (!c) return fail("null context");
     CK(set_factor(c, c->H[c->hcur], c->ldh, c->kp, c->k, c->n_loc, h_host, dtype));
-    c->h_set = true; c->ab_valid = false;
+    c->h_set = true; c->ab_valid = false; c->tc.hs_valid[c->hcur] = false;
     return 0;
 }
 int pymfb_get_w(pymfb_ctx* c, void* w_host, int dtype) {
@@ -707,7 +707,7 @@ int pymfb_gen_h(pymfb_ctx* c, uint64_t seed) {
     k_gen_uniform<<<grid_for((int64_t)c->k * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(c->H[c->hcur], c->ldh, c->k, c->n_loc, seed, c->n_glob, c->col0);
     c->launches += 1;
     CU(cudaGetLastError());
-    c->h_set = true; c->ab_valid = false;
+    c->h_set = true; c->ab_valid = false; c->tc.hs_valid[c->hcur] = false;
     return 0;
 }
 
@@ -739,6 +739,7 @@ int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n
         CU(cudaMemsetAsync(&c->st->stop, 0, sizeof(int), c->stream));
         c->g_valid = false;   // recomputed lazily for the surviving W
         c->ab_valid = false;
+        c->tc.hs_valid[0] = c->tc.hs_valid[1] = false;
     }
     if (do_e && nf > 0) CU(cudaMemcpyAsync(ferr_host, c->ferr_dev, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

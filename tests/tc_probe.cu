@@ -64,7 +64,7 @@ int main() {
         printf(" h_update tile0 max rel err vs exact = %.3e\n", maxerr);
 
         // ---- X H^T: P[row][j] = sum_c x(row,c) h(j,c)
-        float* dP; CHECK(cudaMalloc(&dP, d * KP * 4)); CHECK(cudaMemset(dP, 0, d * KP * 4));
+        float* dP; CHECK(cudaMalloc(&dP, (d * KP + KP * KP) * 4)); CHECK(cudaMemset(dP, 0, (d * KP + KP * KP) * 4));
         CHECK(cudaMemset(dbg, 0xFF, 128 * 4 * KP * 4));
         if (tc_xht(p, st, dH0, dP, 0, &launches)) { printf("launch failed\n"); return 1; }
         e = cudaDeviceSynchronize();
@@ -81,6 +81,17 @@ int main() {
             maxerr = std::max(maxerr, std::fabs(P[r * KP + j] - a) / (std::fabs(a) + 1e-30));
         }
         printf("   xht P max rel err vs exact = %.3e   (P[0][0]=%g P[5][3]=%g P[200][31]=%g)\n", maxerr, P[0], P[5 * KP + 3], P[200 * KP + 31]);
+        {   // H H^T block (TS kernels only): B[i][j] = sum_c h(i,c) h(j,c)
+            std::vector<float> Bm(KP * KP);
+            CHECK(cudaMemcpy(Bm.data(), dP + d * KP, Bm.size() * 4, cudaMemcpyDeviceToHost));
+            double be = 0;
+            for (int i = 0; i < KP; ++i) for (int j = 0; j < KP; ++j) {
+                double a = 0;
+                for (int64_t c = 0; c < n; ++c) a += (double)cs.h(i, c) * cs.h(j, c);
+                be = std::max(be, std::fabs(Bm[i * KP + j] - a) / (std::fabs(a) + 1e-30));
+            }
+            printf("   H H^T max rel err vs exact = %.3e (use_ts=%d)\n", be, (int)p.use_ts);
+        }
         cudaFree(dX); cudaFree(dW); cudaFree(dH0); cudaFree(dH1); cudaFree(dG); cudaFree(dP);
         tc_release(p);
     }
