@@ -40,6 +40,8 @@
 namespace pymfb {
 namespace tc {
 
+constexpr int NPROD = 3;              // TMA producer warps (stages round-robin): ONE issuing thread sustains only
+                                      // ~58 GB/s of TMA traffic (measured, tests/tc_probe l2bw), 4 reach 130-190 GB/s per SM
 constexpr int R1 = 32;                // rows (contraction) per stage of the H-update pass
 constexpr int TILE_COLS = 128;        // columns per tile = UMMA M of the H-update pass
 constexpr int XSTAGE_BYTES = 128 * 32 * 4;   // 16 KB: 128 x 32 fp32 in either orientation
@@ -192,7 +194,7 @@ struct HCfg {   // H-update pass
     static constexpr int SEG_COLS = 2 * KP;                         // [hi | small] per segment buffer
     static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;               // 2 warps per TMEM lane quarter for wide k
     static constexpr int NJ = KP / (EPI_WARPS / 4);                 // basis columns per epilogue thread
-    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
+    static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
     static_assert(STAGES >= 2, "not enough shared memory for two stages");
@@ -235,7 +237,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -247,13 +249,14 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
     auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
 
-    if (warp == 0) {
+    if (warp < NPROD) {
         // ===== TMA producer =====
         {
-            int s = 0; uint32_t ph = 0;
+            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int col0 = tile * TILE_COLS;
                 for (int it = 0; it < nit; ++it) {
+                    if (pcnt++ % NPROD == (uint32_t)warp) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::WSTAGE_BYTES);
@@ -267,11 +270,12 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
                     }
                     __syncwarp();
+                    }
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == NPROD) {
         // ===== MMA issuer =====
         {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
@@ -312,9 +316,9 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < NPROD + 5) {
         // ===== split warps: lo tiles (and masked hi) of the X / H operand =====
-        const int tid_s = threadIdx.x - 64;
+        const int tid_s = threadIdx.x - 32 * (NPROD + 1);
         int s = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int it = 0; it < nit; ++it) {
@@ -331,7 +335,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     } else {
         // ===== epilogue warps: drain segments into registers, then the H update =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int jbase = ((warp - 6) >> 2) * Cfg::NJ;   // basis columns [jbase, jbase + NJ) of this warp
+        const int jbase = ((warp - (NPROD + 5)) >> 2) * Cfg::NJ;   // basis columns [jbase, jbase + NJ) of this warp
         const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
@@ -396,7 +400,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
 template <int KP>
@@ -408,7 +412,7 @@ struct XCfg {   // X H^T pass
     static constexpr int SEG_COLS = 2 * KP;                         // [hi | small]
     static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;
     static constexpr int NJ = KP / (EPI_WARPS / 4);
-    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
+    static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
     static_assert(NJ % 16 == 0, "epilogue column split must be a multiple of 16");
@@ -445,7 +449,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -461,14 +465,15 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         return (c_end - c_begin + 31) / 32;
     };
 
-    if (warp == 0) {
+    if (warp < NPROD) {
         {
-            int s = 0; uint32_t ph = 0;
+            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
             for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
                 int c_begin;
                 const int nch = task_chunks(task, c_begin);
                 const int row0 = (task % num_rb) * 128;
                 for (int ch = 0; ch < nch; ++ch) {
+                    if (pcnt++ % NPROD == (uint32_t)warp) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
@@ -476,11 +481,12 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                         tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);   // [H_hi ; H_lo] rows
                     }
                     __syncwarp();
+                    }
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == NPROD) {
         {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
@@ -521,8 +527,8 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp < 6) {
-        const int tid_s = threadIdx.x - 64;
+    } else if (warp < NPROD + 5) {
+        const int tid_s = threadIdx.x - 32 * (NPROD + 1);
         int s = 0; uint32_t ph = 0;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
             int c_begin;
@@ -540,7 +546,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         }
     } else {
         const int q = warp & 3;
-        const int jbase = ((warp - 6) >> 2) * Cfg::NJ;
+        const int jbase = ((warp - (NPROD + 5)) >> 2) * Cfg::NJ;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
@@ -583,7 +589,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
 // =============================================================================================
@@ -629,7 +635,7 @@ struct TsCfg {
     static constexpr int NT = NT_RAW > 6 ? 6 : NT_RAW;
     static constexpr int EPI_WARPS = 4;
     static constexpr int NJ = KP;
-    static constexpr int THREADS = 32 * (6 + EPI_WARPS);
+    static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
     static constexpr int NBAR = 2 * STAGES + 2 * NT + 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
     static_assert(KP == 32 || KP == 64, "TS kernels serve KP = 32 and 64");
@@ -678,7 +684,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -689,28 +695,36 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                    // [32 rows][128 cols] plain
     auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };        // MN-major chunks
 
-    if (warp == 0) {
+    if (warp < NPROD) {
         {
-            int s = 0; uint32_t ph = 0;
+            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int col0 = tile * TILE_COLS;
                 for (int it = 0; it < nit; ++it) {
+                    if (pcnt++ % NPROD == (uint32_t)warp) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     if (elect_one()) {
+#if defined(PYMFB_EXP_SKIP_WLOAD)
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES);
+#else
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::BSTAGE_BYTES);
+#endif
                         const bool xphase = it < nd;
                         const int r0 = (xphase ? it : it - nd) * R1;
                         tma_load_2d(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0);
+#if !defined(PYMFB_EXP_SKIP_WLOAD)
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
                         for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+#endif
                     }
                     __syncwarp();
+                    }
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == NPROD) {
         {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
@@ -733,8 +747,12 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
                             for (int kg = 0; kg < R1 / 8; ++kg) {
                                 const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
+#if !defined(PYMFB_EXP_SKIP_MMA)
                                 umma_tf32_ts(dcol, a_hi + kg * 8, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
+#if !defined(PYMFB_EXP_ONE_MMA)
                                 umma_tf32_ts(dcol + KP, a_hi + 32 + kg * 8, bd, idesc_h, 1u);
+#endif
+#endif
                             }
                             umma_commit(empty_bar(s));
                             umma_commit(aempty_bar(t));
@@ -750,7 +768,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < NPROD + 5) {
         // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
         const int q = warp & 3;
         const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
@@ -761,12 +779,14 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 mbar_wait(full_bar(s), ph);
                 mbar_wait(aempty_bar(t), tph ^ 1);
                 tc_fence_after();
+#if !defined(PYMFB_EXP_SKIP_CONVERT)
                 const float* xs = reinterpret_cast<const float*>(smem_gen + s * Cfg::STAGE_BYTES);
                 float v[32];
 #pragma unroll
                 for (int r = 0; r < 32; ++r) v[r] = xs[r * TILE_COLS + mylane];
                 park_hilo(lane_addr + t * 64, v);
                 tmem_st_wait();
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull_bar(t));
@@ -783,6 +803,12 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             float creg[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) creg[j] = 0.f;
+            // Old H of this lane's column, fetched NOW: under a saturated memory system a dependent
+            // global load takes ~3 us, and doing it after the last segment stalled every tile by ~10 us.
+            const int col = tile * TILE_COLS + q * 32 + lane;
+            float hreg[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
@@ -806,7 +832,6 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
-                const int col = tile * TILE_COLS + q * 32 + lane;
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
                     float dh[16], dl[16];
@@ -818,11 +843,15 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) { o[j] = creg[j0 + j]; o[KP + j] = dh[j] + dl[j]; }
                     }
+#if defined(PYMFB_EXP_SKIP_EPI_GLOBAL)
+                    if (col < -1) {
+#else
                     if (col < n_loc) {
+#endif
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
-                            const float h = Hc[o];
+                            const float h = hreg[j0 + j];
                             const float hn = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
@@ -840,11 +869,11 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
 constexpr int X_CONV_GROUPS = 2;                          // convert-warp groups of the X.H^T pass (alternate stages)
-constexpr int X_THREADS = 32 * (2 + 4 * X_CONV_GROUPS + 4);
+constexpr int X_THREADS = 32 * (NPROD + 1 + 4 * X_CONV_GROUPS + 4);
 
 // X H^T pass, TS variant.  Tasks [0, x_tasks): (128-row block of X, column range) -> P_A += X H^T.
 // Tasks [x_tasks, num_tasks): column ranges of H itself as the A operand -> P_B += H H^T (same code,
@@ -874,7 +903,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int EPI_WARP0 = 2 + 4 * X_CONV_GROUPS;
+    constexpr int EPI_WARP0 = NPROD + 1 + 4 * X_CONV_GROUPS;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapHs); tma_prefetch_desc(&mapHA);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -882,7 +911,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -901,24 +930,26 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         return (c_end - c_begin + 31) / 32;
     };
 
-    if (warp == 0) {
-        int s = 0; uint32_t ph = 0;
+    if (warp < NPROD) {
+        int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
             int c_begin, row0; bool hh;
             const int nch = task_info(task, c_begin, row0, hh);
             const CUtensorMap* ma = hh ? &mapHA : &mapX;
             for (int ch = 0; ch < nch; ++ch) {
-                mbar_wait(empty_bar(s), ph ^ 1);
+                if (pcnt++ % NPROD == (uint32_t)warp) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
                     tma_load_2d(xs_addr(s), ma, full_bar(s), c_begin + 32 * ch, row0);
                     tma_load_2d(hch(s), &mapHs, full_bar(s), c_begin + 32 * ch, 0);
                 }
                 __syncwarp();
+                    }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == NPROD) {
         constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
         constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
         int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
@@ -962,7 +993,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         // convert warps: thread <-> row of the X block (TMEM lane); reads its 128 B row (SW128: 16 B
         // chunk j sits at (j ^ (row & 7))), splits in registers, parks hi/lo in the TMEM A ring.
         const int q = warp & 3;
-        const int group = (warp - 2) >> 2;
+        const int group = (warp - (NPROD + 1)) >> 2;
         const int myrow = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
         uint32_t c = 0;                                     // stage counter of this CTA
@@ -1034,7 +1065,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
 // H (kp x ldh) -> Hs = [H_hi rows ; H_lo rows] (2kp x ldh); used when the X.H^T pass runs on an H that
@@ -1208,6 +1239,11 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     p.x_rb = (int)((d + 127) / 128);
     const int64_t chunks = (n_loc + 31) / 32;
     int64_t splits = std::max<int64_t>(1, (4LL * sm_count + p.x_rb - 1) / p.x_rb);
+    {   // make #tasks a multiple of the CTA count: 608 tasks on 148 CTAs ran 5 rounds with the last 11 % full
+        auto gcd = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+        const int64_t m = sm_count / gcd(p.x_rb, sm_count);
+        splits = std::max<int64_t>(m, (splits + m / 2) / m * m);
+    }
     splits = std::min(splits, chunks);
     const int64_t chunks_per = (chunks + splits - 1) / splits;
     p.x_cols_per_task = (int)(chunks_per * 32);
