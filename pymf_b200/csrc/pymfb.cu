@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fused.cuh"
 
 using namespace pymfb;
 
@@ -141,6 +142,7 @@ struct pymfb_ctx {
     int path_opt = PYMFB_PATH_AUTO;
     int path = PYMFB_PATH_SIMT;
     TcPlan tc;                     // tensor-core plan (kernels_tc.cuh)
+    FusedPlan fused;               // one-pass kernel plan (kernels_fused.cuh)
 
     void* comm = nullptr;
     int world = 1, rank = 0;
@@ -159,6 +161,14 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 static inline int grid_for(int64_t count, int block, int cap) {
     int64_t g = (count + block - 1) / block;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+static int plan_tc(pymfb_ctx* c) {
+    if (tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1]))
+        return fail("tcgen05 plan failed: %s", c->tc.err.c_str());
+    fused_release(c->fused);
+    if (fused_wanted(c->tc) && fused_plan(c->fused, c->tc)) return fail("fused-kernel plan failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
 }
 
 static int timing_begin(pymfb_ctx* c, int which, cudaEvent_t* e0, cudaEvent_t* e1) {
@@ -246,6 +256,22 @@ static int launch_h_update(pymfb_ctx* c) {
     CK(timing_end(c, 0, e0, e1));
     c->hcur ^= 1;
     c->ab_valid = false;
+    return 0;
+}
+
+// One-pass iteration body (kernels_fused.cuh): H[hcur] -> H[hcur^1], P = [X H^T | H H^T], AB = allreduce(P)
+static int launch_fused(pymfb_ctx* c) {
+    k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
+    c->launches += 1;
+    cudaEvent_t e0, e1;
+    CK(timing_begin(c, 0, &e0, &e1));
+    if (fused_launch(c->fused, c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->G, c->P, c->stream, &c->launches))
+        return fail("fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(timing_end(c, 0, e0, e1));
+    c->hcur ^= 1;
+    if (c->world > 1)
+        NC(g_nccl.AllReduce(c->P, c->AB, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
+    c->ab_valid = true;
     return 0;
 }
 
@@ -356,9 +382,14 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
         }
         if (do_h) {
             if (!c->g_valid) CK(launch_gram_w(c));
-            CK(launch_h_update(c));
             // A, B of the new H feed the next W update and this iteration's error
-            if (trace || (do_w && i + 1 < niter)) CK(launch_xht(c));
+            const bool need_ab = trace || (do_w && i + 1 < niter);
+            if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready) {
+                CK(launch_fused(c));
+            } else {
+                CK(launch_h_update(c));
+                if (need_ab) CK(launch_xht(c));
+            }
         }
         if (do_e) {
             if (trace && !c->g_valid) CK(launch_gram_w(c));
@@ -444,6 +475,7 @@ int pymfb_destroy(pymfb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     tc_release(c->tc);
+    fused_release(c->fused);
     for (int w = 0; w < 2; ++w)
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->AB != c->P) cudaFree(c->AB);
@@ -460,7 +492,7 @@ int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
     if (option == PYMFB_OPT_PATH) {
         if (value < 0 || value > 2) return fail("bad path option %lld", (long long)value);
         c->path_opt = (int)value;
-        if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC && tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1])) return fail("tcgen05 plan failed: %s", c->tc.err.c_str()); c->g_valid = false; }
+        if (c->X) { CK(resolve_path(c)); if (c->path == PYMFB_PATH_TC) CK(plan_tc(c)); c->g_valid = false; }
         return 0;
     }
     if (option == PYMFB_OPT_ERR_MODE) {
@@ -506,7 +538,7 @@ int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
 static int data_changed(pymfb_ctx* c) {
     c->ab_valid = false; c->xx_valid = false;
     CK(resolve_path(c));
-    if (c->path == PYMFB_PATH_TC && tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1])) return fail("tcgen05 plan failed: %s", c->tc.err.c_str());
+    if (c->path == PYMFB_PATH_TC) CK(plan_tc(c));
     c->g_valid = false;
     return 0;
 }

@@ -243,3 +243,30 @@ def test_tensor_core_path_matches_fp32_path(shape):
     # the two kernel families agree far below the tolerance (3xTF32 ~ fp32 accuracy)
     assert rel(res["tc"][0], res["simt"][0]) < 2e-5
     assert rel(res["tc"][1], res["simt"][1]) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(512, 4096, 32), (1000, 5000, 20), (4096, 8192, 32), (300, 1100, 32)])
+def test_fused_one_pass_kernel_matches_two_pass(shape, monkeypatch):
+    """kernels_fused.cuh (H update + X.H^T + H.H^T with X read once) vs the two-pass tensor-core
+    kernels vs the float64 oracle; PYMFB_FUSED forces / disables the fused kernel."""
+    d, n, k = shape
+    rng = np.random.RandomState(d + n)
+    X = rng.random_sample((d, n)).astype(np.float32)
+    W0 = rng.random_sample((d, k)); H0 = rng.random_sample((k, n))
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=4, early_stop=False)
+    res = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("PYMFB_FUSED", fused)
+        e = pymf_b200.Engine(d, n, k, path="tc")
+        try:
+            e.set_err_mode("trace")
+            e.upload_x(X); e.set_w(W0); e.set_h(H0)
+            f, done = e.run(4, early_stop=False)
+            res[fused] = (e.get_w(), e.get_h(), f)
+        finally:
+            e.close()
+        W, H, f = res[fused]
+        assert rel(W, Wr) < TOL_WH and rel(H, Hr) < TOL_WH, (fused, rel(W, Wr), rel(H, Hr))
+        assert np.max(np.abs(f - fr) / fr) < TOL_FERR, fused
+    assert rel(res["1"][0], res["0"][0]) < 2e-5 and rel(res["1"][1], res["0"][1]) < 2e-5
