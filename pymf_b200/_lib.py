@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpymfb.so")
+# PYMFB_LIB: alternative build of the same library (kernel experiments: ablation variants built with
+# PYMFB_NVCC_EXTRA / PYMFB_OUT); the default is the in-tree product library.
+LIB_PATH = os.environ.get("PYMFB_LIB") or os.path.join(_HERE, "libpymfb.so")
 
 F32, F64 = 0, 1
 COMPUTE_W, COMPUTE_H, COMPUTE_ERR, EARLY_STOP = 1, 2, 4, 8

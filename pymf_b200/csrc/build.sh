@@ -5,5 +5,5 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
   -Xcompiler -fPIC -Xcompiler -Wall -shared ${PYMFB_NVCC_EXTRA} \
-  -o ../libpymfb.so pymfb.cu -ldl -lpthread
-echo "built $(cd .. && pwd)/libpymfb.so"
+  -o ${PYMFB_OUT:-../libpymfb.so} pymfb.cu -ldl -lpthread
+echo "built ${PYMFB_OUT:-$(cd .. && pwd)/libpymfb.so}"

@@ -28,9 +28,8 @@ namespace pymfb {
 namespace tc {
 
 constexpr int F_KP = 32;
-constexpr int F_SBC = 1024;                 // super-block columns
-constexpr int F_TILES_PER_SB = F_SBC / TILE_COLS;
-constexpr int F_NSLOT = 4;                  // C_part ring depth in super-blocks
+// super-block columns (sbc), tiles per super-block and the C_part ring depth (nslot) are run-time
+// parameters of the plan (FusedParams) so that the L2 window = (lag + 1) x d x sbc x 4 B can be tuned.
 constexpr int F_CONV_GROUPS = 2;
 constexpr int F_WARPS = NPROD + 1 + 4 * F_CONV_GROUPS + 4 + 4;
 constexpr int F_THREADS = 32 * F_WARPS;
@@ -47,13 +46,17 @@ struct FusedParams {
     const float* G;         // W^T W (kp x kp, fp32)
     float* PA;              // d x kp   (+= X Hn^T)
     float* PB;              // kp x kp  (+= Hn Hn^T)
-    float* Cpart;           // [F_NSLOT][F_SBC][kp] fp32 accumulator of the slab partials (zero between uses)
+    float* Cpart;           // [nslot][sbc][kp] fp32 accumulator of the slab partials (zero between uses)
     int* tile_cnt;          // [n_tiles]   slabs arrived per tile
     int* sb_cnt;            // [n_sb]      tiles updated per super-block
     int64_t ldh;
     int d, n_loc, n_tiles, n_sb, num_rb;
     int nslab, slab_rows;
-    int nA, nB;             // A / B tasks per super-block (nA = F_TILES_PER_SB * nslab, nB = num_rb + 1)
+    int sbc, tiles_per_sb, nslot;
+    int bcols, nbsplit;     // B tasks cover bcols columns of a super-block (nbsplit = sbc / bcols parts)
+    int* tile_done;         // [n_tiles] 1 once the tile's new H (and its hi/lo split) is visible
+    int hint;               // 1: L2 cache hints on the X loads (first read evict_last, second read evict_first)
+    int nA, nB;             // A / B tasks per super-block (nA = tiles_per_sb * nslab, nB = num_rb + 1)
     int lag;                // B tasks of super-block s run in step s + lag
     int num_tasks;
 };
@@ -65,6 +68,7 @@ struct FTask {
     int slab;      // A
     int rb;        // B: row block (== num_rb -> H H^T)
     int nst;       // stages
+    int c0;        // B: first column
 };
 
 // global task index -> task.  Step s holds the A tasks of super-block s (s < n_sb) interleaved with the
@@ -72,7 +76,7 @@ struct FTask {
 // depends on, so its wait is normally already satisfied; X stays in L2 for (lag + 1) super-blocks.
 __device__ __forceinline__ FTask f_decode(const FusedParams& p, int idx) {
     FTask t;
-    t.type = -1; t.sb = 0; t.tile = 0; t.slab = 0; t.rb = 0; t.nst = 0;
+    t.type = -1; t.sb = 0; t.tile = 0; t.slab = 0; t.rb = 0; t.nst = 0; t.c0 = 0;
     const int T = p.nA + p.nB;
     const int headN = p.lag * p.nA, midN = (p.n_sb - p.lag) * T;
     int step, pos;
@@ -91,7 +95,7 @@ __device__ __forceinline__ FTask f_decode(const FusedParams& p, int idx) {
     }
     if (!isB) {
         t.sb = step;
-        t.tile = step * F_TILES_PER_SB + local / p.nslab;
+        t.tile = step * p.tiles_per_sb + local / p.nslab;
         t.slab = local % p.nslab;
         if (t.tile >= p.n_tiles) return t;
         const int r0 = t.slab * p.slab_rows;
@@ -99,9 +103,15 @@ __device__ __forceinline__ FTask f_decode(const FusedParams& p, int idx) {
         t.nst = (r1 - r0 + R1 - 1) / R1;
         t.type = 0;
     } else {
+        // part-major: the B tasks of the first columns of a super-block come first (their tiles are
+        // the first to be updated)
         t.sb = step - p.lag;
-        t.rb = local;
-        const int c0 = t.sb * F_SBC, c1 = min(p.n_loc, c0 + F_SBC);
+        const int part = local / (p.num_rb + 1);
+        t.rb = local % (p.num_rb + 1);
+        const int c0 = t.sb * p.sbc + part * p.bcols;
+        const int c1 = min(p.n_loc, min(c0 + p.bcols, (t.sb + 1) * p.sbc));
+        if (c0 >= c1) return t;
+        t.c0 = c0;
         t.nst = (c1 - c0 + 31) / 32;
         t.type = 1;
     }
@@ -120,6 +130,22 @@ __device__ __forceinline__ void spin_until_ge(const int* p, int want) {
         __nanosleep(200);
         if (clock64() - t0 > 8000000000LL) __trap();
     }
+}
+// TMA load with an L2 eviction-priority hint (createpolicy.fractional.L2::evict_*)
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -200,13 +226,14 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
     if (warp < NPROD) {
         // ===== TMA producers (stage pcnt % NPROD == warp) =====
         uint32_t pcnt = 0;
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
         for (int idx = blockIdx.x; idx < p.num_tasks; idx += gridDim.x) {
             const FTask t = f_decode(p, idx);
             if (t.type < 0) continue;
             if (t.type == 1) {
-                // every tile of the super-block must have been updated (Hn / Hs final)
-                const int want = min(F_TILES_PER_SB, p.n_tiles - t.sb * F_TILES_PER_SB);
-                spin_until_ge(p.sb_cnt + t.sb, want);
+                // every tile this task reads must have been updated (Hn / Hs final)
+                const int tl0 = t.c0 / TILE_COLS, tl1 = min(p.n_tiles - 1, (t.c0 + 32 * t.nst - 1) / TILE_COLS);
+                for (int tl = tl0; tl <= tl1; ++tl) spin_until_ge(p.tile_done + tl, 1);
                 fence_proxy_async_all();        // generic-proxy stores of other CTAs -> our async-proxy (TMA) reads
             }
             for (int it = 0; it < t.nst; ++it, ++pcnt) {
@@ -218,14 +245,17 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                     mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::BSTAGE_BYTES);
                     if (t.type == 0) {
                         const int r0 = t.slab * p.slab_rows + it * R1;
-                        tma_load_2d(xs_addr(s), &mapXp, full_bar(s), t.tile * TILE_COLS, r0);
+                        if (p.hint) tma_load_2d_hint(xs_addr(s), &mapXp, full_bar(s), t.tile * TILE_COLS, r0, pol_keep);
+                        else tma_load_2d(xs_addr(s), &mapXp, full_bar(s), t.tile * TILE_COLS, r0);
                         tma_load_2d(bop(s), &mapW, full_bar(s), 0, r0);
                         tma_load_2d(bop(s) + R1 * 128, &mapW, full_bar(s), 32, r0);
                     } else {
-                        const int c0 = t.sb * F_SBC + 32 * it;
-                        if (t.rb < p.num_rb) tma_load_2d(xs_addr(s), &mapXx, full_bar(s), c0, t.rb * 128);
-                        else tma_load_2d(xs_addr(s), &mapHa, full_bar(s), c0, 0);
-                        tma_load_2d(bop(s), &mapHs, full_bar(s), c0, 0);
+                        const int c0 = t.c0 + 32 * it;
+                        if (t.rb < p.num_rb) {
+                            if (p.hint) tma_load_2d_hint(xs_addr(s), &mapXx, full_bar(s), c0, t.rb * 128, pol_drop);
+                            else tma_load_2d(xs_addr(s), &mapXx, full_bar(s), c0, t.rb * 128);
+                        } else tma_load_2d(xs_addr(s), &mapHa, full_bar(s), c0, 0);
+                        tma_load_2d(bop(s), &mapHs, full_bar(s), 0, (c0 >> 5) * (2 * KP));
                     }
                 }
                 __syncwarp();
@@ -258,15 +288,17 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
 #pragma unroll
                             for (int kg = 0; kg < 4; ++kg) {
                                 const uint64_t bd = make_desc(bop(s) + kg * 1024, R1 * 128, 512, 1);
-                                umma_tf32_ts(dcol, a_hi + kg * 8, bd, idA_hl, (first && kg == 0) ? 0u : 1u);
-                                umma_tf32_ts(dcol + KP, a_hi + 32 + kg * 8, bd, idA_h, 1u);
+                                const uint32_t dc = dcol + (kg % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
+                                umma_tf32_ts(dc, a_hi + kg * 8, bd, idA_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
+                                umma_tf32_ts(dc + KP, a_hi + 32 + kg * 8, bd, idA_h, 1u);
                             }
                         } else {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t bd = make_desc(bop(s) + ks * 32, 16, 1024);
-                                umma_tf32_ts(dcol, a_hi + ks * 8, bd, idB_hl, (first && ks == 0) ? 0u : 1u);
-                                umma_tf32_ts(dcol + KP, a_hi + 32 + ks * 8, bd, idB_h, 1u);
+                                const uint32_t dc = dcol + (ks % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
+                                umma_tf32_ts(dc, a_hi + ks * 8, bd, idB_hl, (first && ks < Cfg::NCHAIN) ? 0u : 1u);
+                                umma_tf32_ts(dc + KP, a_hi + 32 + ks * 8, bd, idB_h, 1u);
                             }
                         }
                         umma_commit(empty_bar(s));
@@ -349,12 +381,15 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
-                    float hi[16], sm[16];
-                    tmem_ld16(taddr + j0, hi);
-                    tmem_ld16(taddr + KP + j0, sm);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j0 + j] += hi[j] + sm[j];
+                    for (int ch = 0; ch < Cfg::NCHAIN; ++ch) {
+                        float hi[16], sm[16];
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + j0, hi);
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + KP + j0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j0 + j] += hi[j] + sm[j];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -362,7 +397,7 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
             }
             if (t.type == 0) {
                 // partial C of (tile, slab): [slot][slab][column in sb][KP]
-                if (t.sb >= F_NSLOT && et == 0) spin_until_ge(p.sb_cnt + (t.sb - F_NSLOT), min(F_TILES_PER_SB, p.n_tiles - (t.sb - F_NSLOT) * F_TILES_PER_SB));
+                if (t.sb >= p.nslot && et == 0) spin_until_ge(p.sb_cnt + (t.sb - p.nslot), min(p.tiles_per_sb, p.n_tiles - (t.sb - p.nslot) * p.tiles_per_sb));
                 named_bar_sync(1, 128);
                 // fp32 REDs into the L2-resident accumulator [slot][column in sb][KP] (zero on entry: the
                 // update warps clear every block they consume).  Transposed through shared memory so that
@@ -371,8 +406,8 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                 for (int j = 0; j < KP; ++j) tr[lane * 33 + j] = acc[j];
                 __syncwarp();
                 {
-                    const int csb0 = (t.tile % F_TILES_PER_SB) * TILE_COLS + q * 32;
-                    float* dst = p.Cpart + ((size_t)(t.sb % F_NSLOT) * F_SBC + csb0) * KP + lane;
+                    const int csb0 = (t.tile % p.tiles_per_sb) * TILE_COLS + q * 32;
+                    float* dst = p.Cpart + ((size_t)(t.sb % p.nslot) * p.sbc + csb0) * KP + lane;
 #pragma unroll 8
                     for (int r = 0; r < 32; ++r) atomicAdd(dst + r * KP, tr[r * 33 + lane]);
                 }
@@ -425,20 +460,20 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
             if (lane == 0) mbar_arrive(uqempty_bar(u));
             ++uq;
             if (tile < 0) break;
-            const int sb = tile / F_TILES_PER_SB;
+            const int sb = tile / p.tiles_per_sb;
             const int col = tile * TILE_COLS + ut;
-            const int csb = (tile % F_TILES_PER_SB) * TILE_COLS + ut;
+            const int csb = (tile % p.tiles_per_sb) * TILE_COLS + ut;
             float cs[KP];
             __threadfence();
             {
-                float4* src = reinterpret_cast<float4*>(p.Cpart + ((size_t)(sb % F_NSLOT) * F_SBC + csb) * KP);
+                float4* src = reinterpret_cast<float4*>(p.Cpart + ((size_t)(sb % p.nslot) * p.sbc + csb) * KP);
 #pragma unroll
                 for (int j = 0; j < KP; j += 4) {
                     const float4 v = __ldcg(src + j / 4);
                     cs[j] = v.x; cs[j + 1] = v.y; cs[j + 2] = v.z; cs[j + 3] = v.w;
                 }
 #pragma unroll
-                for (int j = 0; j < KP; j += 4) __stcg(src + j / 4, make_float4(0.f, 0.f, 0.f, 0.f));   // ready for sb + F_NSLOT
+                for (int j = 0; j < KP; j += 4) __stcg(src + j / 4, make_float4(0.f, 0.f, 0.f, 0.f));   // ready for sb + nslot
             }
             if (col < p.n_loc) {
                 float h[KP];
@@ -453,14 +488,14 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                     const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                     const int64_t o = (int64_t)j * p.ldh + col;
                     p.Hn[o] = hn;
-                    p.Hs[o] = hh;
-                    p.Hs[o + (int64_t)KP * p.ldh] = hn - hh;
+                    p.Hs[hs_index(j, col, 2 * KP)] = hh;
+                    p.Hs[hs_index(KP + j, col, 2 * KP)] = hn - hh;
                 }
             }
             __threadfence();
             fence_proxy_async_all();
             named_bar_sync(2, 128);
-            if (ut == 0) atomicAdd(p.sb_cnt + sb, 1);
+            if (ut == 0) { atomicExch(p.tile_done + tile, 1); atomicAdd(p.sb_cnt + sb, 1); }
         }
     }
     tc_fence_before();
@@ -476,8 +511,9 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
 struct FusedPlan {
     bool ready = false;
     float* Cpart = nullptr;
-    int* cnt = nullptr;          // [n_tiles] tile arrivals, then [n_sb] super-block completions
+    int* cnt = nullptr;          // [n_tiles] tile arrivals, [n_sb] super-block completions, [n_tiles] tile done flags
     int n_tiles = 0, n_sb = 0, nslab = 0, slab_rows = 0, nA = 0, nB = 0, lag = 1, num_tasks = 0;
+    int sbc = 1024, tiles_per_sb = 8, nslot = 4, hint = 0, bcols = 1024, nbsplit = 1;
     int smem = 0;
 };
 
@@ -502,21 +538,30 @@ inline bool fused_wanted(const TcPlan& p) {
 inline int fused_plan(FusedPlan& f, const TcPlan& p) {
     fused_release(f);
     f.n_tiles = p.h_tiles;
-    f.n_sb = (int)((p.n_loc + tc::F_SBC - 1) / tc::F_SBC);
-    int nslab = (int)std::max<int64_t>(1, (p.d + 256) / 512);
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    f.sbc = env_int("PYMFB_FUSED_SBC", 1024);
+    f.sbc = std::max(tc::TILE_COLS, f.sbc / tc::TILE_COLS * tc::TILE_COLS);
+    f.tiles_per_sb = f.sbc / tc::TILE_COLS;
+    f.hint = env_int("PYMFB_FUSED_HINT", 0);
+    const int slab_want = std::max(tc::R1, env_int("PYMFB_FUSED_SLAB", 512) / tc::R1 * tc::R1);
+    f.n_sb = (int)((p.n_loc + f.sbc - 1) / f.sbc);
+    int nslab = (int)std::max<int64_t>(1, (p.d + slab_want / 2) / slab_want);
     f.slab_rows = (int)(((p.d + nslab - 1) / nslab + tc::R1 - 1) / tc::R1 * tc::R1);
     f.nslab = (int)((p.d + f.slab_rows - 1) / f.slab_rows);
-    f.nA = tc::F_TILES_PER_SB * f.nslab;
-    f.nB = p.x_rb + 1;
+    f.nA = f.tiles_per_sb * f.nslab;
+    f.bcols = std::min(f.sbc, std::max(32, env_int("PYMFB_FUSED_BCOLS", f.sbc) / 32 * 32));
+    f.nbsplit = (f.sbc + f.bcols - 1) / f.bcols;
+    f.nB = (p.x_rb + 1) * f.nbsplit;
     {
         const char* e = getenv("PYMFB_FUSED_LAG");
         f.lag = e ? atoi(e) : 3;
         f.lag = std::max(1, std::min(f.lag, f.n_sb));
     }
+    f.nslot = f.lag + 4;
     f.num_tasks = f.lag * f.nA + (f.n_sb - f.lag) * (f.nA + f.nB) + f.lag * f.nB;
-    if (cudaMalloc(&f.Cpart, (size_t)tc::F_NSLOT * tc::F_SBC * tc::F_KP * sizeof(float)) != cudaSuccess) return 1;
-    if (cudaMemset(f.Cpart, 0, (size_t)tc::F_NSLOT * tc::F_SBC * tc::F_KP * sizeof(float)) != cudaSuccess) return 1;
-    if (cudaMalloc(&f.cnt, (size_t)(f.n_tiles + f.n_sb) * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&f.Cpart, (size_t)f.nslot * f.sbc * tc::F_KP * sizeof(float)) != cudaSuccess) return 1;
+    if (cudaMemset(f.Cpart, 0, (size_t)f.nslot * f.sbc * tc::F_KP * sizeof(float)) != cudaSuccess) return 1;
+    if (cudaMalloc(&f.cnt, (size_t)(2 * f.n_tiles + f.n_sb) * sizeof(int)) != cudaSuccess) return 1;
     using Cfg = tc::TsCfg<tc::F_KP>;
     f.smem = Cfg::STAGES * Cfg::STAGE_BYTES + tc::F_KP * tc::F_KP * 4 + 4 * 32 * 33 * 4 + 1024 /*barriers, queue*/ + 1024 /*align*/;
     if (cudaFuncSetAttribute(tc::k_fused_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, f.smem) != cudaSuccess) return 1;
@@ -528,11 +573,13 @@ inline int fused_plan(FusedPlan& f, const TcPlan& p) {
 inline int fused_launch(FusedPlan& f, TcPlan& p, const DevState* st, const float* Hc, float* Hn, const float* G, float* P,
                         cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1, hdst = hsrc ^ 1;
-    if (cudaMemsetAsync(f.cnt, 0, (size_t)(f.n_tiles + f.n_sb) * sizeof(int), stream) != cudaSuccess) return 1;
+    if (cudaMemsetAsync(f.cnt, 0, (size_t)(2 * f.n_tiles + f.n_sb) * sizeof(int), stream) != cudaSuccess) return 1;
     tc::FusedParams fp;
     fp.st = st; fp.Hc = Hc; fp.Hn = Hn; fp.Hs = p.Hs[hdst]; fp.G = G; fp.PA = P; fp.PB = P + p.d * p.kp;
-    fp.Cpart = f.Cpart; fp.tile_cnt = f.cnt; fp.sb_cnt = f.cnt + f.n_tiles;
+    fp.Cpart = f.Cpart; fp.tile_cnt = f.cnt; fp.sb_cnt = f.cnt + f.n_tiles; fp.tile_done = f.cnt + f.n_tiles + f.n_sb;
     fp.ldh = p.ldh; fp.d = (int)p.d; fp.n_loc = (int)p.n_loc; fp.n_tiles = f.n_tiles; fp.n_sb = f.n_sb; fp.num_rb = p.x_rb;
+    fp.bcols = f.bcols; fp.nbsplit = f.nbsplit;
+    fp.sbc = f.sbc; fp.tiles_per_sb = f.tiles_per_sb; fp.nslot = f.nslot; fp.hint = f.hint;
     fp.nslab = f.nslab; fp.slab_rows = f.slab_rows; fp.nA = f.nA; fp.nB = f.nB; fp.lag = f.lag; fp.num_tasks = f.num_tasks;
     const int grid = std::min(p.sm_count, f.num_tasks);
     tc::k_fused_ts<<<grid, tc::F_THREADS, f.smem, stream>>>(p.mapX_p, p.mapW, p.mapX_x, p.mapH_x[hdst], p.mapH_a[hdst], fp);

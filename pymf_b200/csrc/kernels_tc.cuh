@@ -176,6 +176,15 @@ __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, 
     }
 }
 
+// [H_hi ; H_lo] companion of H ("Hs", the B operand of the X.H^T pass) is stored CHUNK-MAJOR:
+// element (row j of the 2KP stacked rows, column c) lives at ((c / 32) * 2KP + j) * 32 + c % 32, so one
+// pipeline stage (2KP rows x 32 columns) is ONE contiguous 2KP x 128 B block.  With the row-major layout
+// the 2KP rows of a stage sat ldh * 4 bytes apart - 256 different 2 MB pages per stage at k = 128,
+// n = 2^20 - and the pass ran 2.2x slower on one GPU than on 8 column shards (TLB-bound TMA).
+__host__ __device__ __forceinline__ int64_t hs_index(int j, int64_t col, int kp2) {
+    return ((col >> 5) * kp2 + j) * 32 + (col & 31);
+}
+
 constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "segments" below)
 
 // Segments.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, so a long chain of
@@ -386,8 +395,8 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                             const float hn = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
-                            Hs[o] = hh;                                  // [H_hi ; H_lo] rows for the X.H^T pass
-                            Hs[o + (int64_t)KP * ldh] = hn - hh;
+                            Hs[hs_index((jbase + j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[hs_index(KP + (jbase + j0 + j), col, 2 * KP)] = hn - hh;
                         }
                     }
                 }
@@ -478,7 +487,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
                         tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
-                        tma_load_2d(hch(s), &mapH, full_bar(s), c_begin + 32 * ch, 0);   // [H_hi ; H_lo] rows
+                        tma_load_2d(hch(s), &mapH, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));   // [H_hi ; H_lo] chunk
                     }
                     __syncwarp();
                     }
@@ -622,6 +631,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+#ifndef PYMFB_NCHAIN
+#define PYMFB_NCHAIN 1   // 2 was measured: no change (316 vs 309 us on the per-SM-bound probe), so the default stays 1
+#endif
 template <int KP>
 struct TsCfg {
     static constexpr int NCH = 2 * KP / 32;
@@ -629,8 +641,14 @@ struct TsCfg {
     static constexpr int STAGE_BYTES = XSTAGE_BYTES + BSTAGE_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SEG_COLS = 2 * KP;
-    static constexpr int A_COL0 = 4 * KP;                           // first TMEM column of the A ring
+    // Accumulation chains per segment buffer.  Back-to-back tcgen05.mma into the SAME accumulator are
+    // latency-bound when N is small (a K = 8, N = 64 MMA is 32 tensor cycles but the dependent issue
+    // distance is far longer), so for KP = 32 consecutive K steps alternate between NCHAIN accumulator
+    // sets that the epilogue sums.
+    static constexpr int NCHAIN = (KP == 32) ? PYMFB_NCHAIN : 1;
+    static constexpr int CHAIN_COLS = 2 * KP;                       // [hi | small] of one chain
+    static constexpr int SEG_COLS = CHAIN_COLS * NCHAIN;
+    static constexpr int A_COL0 = 2 * SEG_COLS;                     // first TMEM column of the A ring
     static constexpr int NT_RAW = (512 - A_COL0) / 64;
     static constexpr int NT = NT_RAW > 6 ? 6 : NT_RAW;
     static constexpr int EPI_WARPS = 4;
@@ -747,10 +765,11 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
                             for (int kg = 0; kg < R1 / 8; ++kg) {
                                 const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
+                                const uint32_t dc = dcol + (kg % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
 #if !defined(PYMFB_EXP_SKIP_MMA)
-                                umma_tf32_ts(dcol, a_hi + kg * 8, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                                umma_tf32_ts(dc, a_hi + kg * 8, bd, idesc_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
 #if !defined(PYMFB_EXP_ONE_MMA)
-                                umma_tf32_ts(dcol + KP, a_hi + 32 + kg * 8, bd, idesc_h, 1u);
+                                umma_tf32_ts(dc + KP, a_hi + 32 + kg * 8, bd, idesc_h, 1u);
 #endif
 #endif
                             }
@@ -816,12 +835,15 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
-                    float hi[16], sm[16];
-                    tmem_ld16(taddr + j0, hi);
-                    tmem_ld16(taddr + KP + j0, sm);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                    for (int ch = 0; ch < Cfg::NCHAIN; ++ch) {
+                        float hi[16], sm[16];
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + j0, hi);
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + KP + j0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -838,6 +860,14 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                     tmem_ld16(taddr + j0, dh);
                     tmem_ld16(taddr + KP + j0, dl);
                     tmem_ld_wait();
+                    if (Cfg::NCHAIN > 1) {
+                        float eh[16], el[16];
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + j0, eh);
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + KP + j0, el);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { dh[j] += eh[j]; dl[j] += el[j]; }
+                    }
                     if (dbg != nullptr && tile == 0) {
                         float* o = dbg + (size_t)(q * 32 + lane) * (2 * KP) + j0;
 #pragma unroll
@@ -855,8 +885,8 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                             const float hn = (h * creg[j0 + j]) / ((dh[j] + dl[j]) + kEpsDenom);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
-                            Hs[o] = hh;                                  // [H_hi ; H_lo] rows for the X.H^T pass
-                            Hs[o + (int64_t)KP * ldh] = hn - hh;
+                            Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[hs_index(KP + (j0 + j), col, 2 * KP)] = hn - hh;
                         }
                     }
                 }
@@ -942,7 +972,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 if (elect_one()) {
                     mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
                     tma_load_2d(xs_addr(s), ma, full_bar(s), c_begin + 32 * ch, row0);
-                    tma_load_2d(hch(s), &mapHs, full_bar(s), c_begin + 32 * ch, 0);
+                    tma_load_2d(hch(s), &mapHs, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));
                 }
                 __syncwarp();
                     }
@@ -973,8 +1003,9 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
-                            umma_tf32_ts(dcol, a_hi + ks * 8, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                            umma_tf32_ts(dcol + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
+                            const uint32_t dc = dcol + (ks % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
+                            umma_tf32_ts(dc, a_hi + ks * 8, bd, idesc_hl, (first && ks < Cfg::NCHAIN) ? 0u : 1u);
+                            umma_tf32_ts(dc + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
                         }
                         umma_commit(empty_bar(s));
                         umma_commit(aempty_bar(t));
@@ -1039,12 +1070,15 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
-                    float hi[16], sm[16];
-                    tmem_ld16(taddr + j0, hi);
-                    tmem_ld16(taddr + KP + j0, sm);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) areg[j0 + j] += hi[j] + sm[j];
+                    for (int ch = 0; ch < Cfg::NCHAIN; ++ch) {
+                        float hi[16], sm[16];
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + j0, hi);
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + KP + j0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) areg[j0 + j] += hi[j] + sm[j];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1075,10 +1109,12 @@ __global__ void k_split_rows(const DevState* __restrict__ st, const float* __res
     if (st->stop) return;
     const int64_t total = (int64_t)kp * ldh;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ldh);
+        const int64_t c = i - (int64_t)r * ldh;
         const float v = H[i];
         const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        Hs[i] = hi;
-        Hs[i + total] = v - hi;
+        Hs[hs_index(r, c, 2 * kp)] = hi;
+        Hs[hs_index(kp + r, c, 2 * kp)] = v - hi;
     }
 }
 
@@ -1108,7 +1144,7 @@ struct TcPlan {
     int k = 0, kp = 0;
     const float* X = nullptr;
     const float* Hbuf[2] = {nullptr, nullptr};
-    float* Hs[2] = {nullptr, nullptr};        // [H_hi ; H_lo] (2kp x ldh) companion of each H buffer
+    float* Hs[2] = {nullptr, nullptr};        // [H_hi ; H_lo] companion of each H buffer, chunk-major (hs_index)
     bool hs_valid[2] = {false, false};
     float* Wsplit = nullptr;   // d x 2kp  [W_hi | W_lo]
     float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
@@ -1221,7 +1257,7 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, true, &p.err);
     for (int i = 0; i < 2; ++i) {
         ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
-        ok = ok && make_map(&p.mapH_x[i], p.Hs[i], 2 * kp, n_loc, ldh, 2 * kp, false, &p.err);   // [H_hi ; H_lo] as B
+        ok = ok && make_map(&p.mapH_x[i], p.Hs[i], (ldh / 32) * 2 * kp, 32, 32, 2 * kp, false, &p.err);   // [H_hi ; H_lo] chunks as B
         ok = ok && make_map(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 128, false, &p.err);        // H as A
     }
     ok = ok && make_map_plain(&p.mapX_p, X, d, n_loc, ldx, tc::TILE_COLS, tc::R1, &p.err);
@@ -1243,6 +1279,16 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         auto gcd = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
         const int64_t m = sm_count / gcd(p.x_rb, sm_count);
         splits = std::max<int64_t>(m, (splits + m / 2) / m * m);
+    }
+    {   // long tasks let the CTAs that share a column range drift apart until the [H_hi ; H_lo] stages they
+        // share fall out of L2 (cfg3 on one GPU: 28 K columns per task ran 50 ms against 23 ms for 8 shards
+        // of 3.5 K columns): cap a task at ~4 K columns, keeping the task count a multiple of the CTA count
+        auto gcd = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+        const int64_t m = sm_count / gcd(p.x_rb, sm_count);
+        if ((chunks + splits - 1) / splits * 32 > 8192) {
+            const int64_t want = (n_loc + 4095) / 4096;
+            splits = std::max<int64_t>(m, (want + m - 1) / m * m);
+        }
     }
     splits = std::min(splits, chunks);
     const int64_t chunks_per = (chunks + splits - 1) / splits;

@@ -158,6 +158,14 @@ struct pymfb_ctx {
 // d * n_local * kp at or below which the error is a direct residual pass (2^28 MACs ~ a few us)
 static const double kDirectErrMaxWork = 268435456.0;
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+// Leading dimension of a row-major matrix with n columns: a multiple of 32 floats, plus PYMFB_LD_PAD floats
+// (experiment knob, default 0) when the plain value is a large power-of-two multiple.
+static inline int64_t padded_ld(int64_t n) {
+    int64_t ld = round_up(n, 32);
+    static const int64_t pad = [] { const char* e = getenv("PYMFB_LD_PAD"); return e ? (int64_t)atoll(e) : (int64_t)0; }();
+    if (pad > 0 && ld % 4096 == 0) ld += round_up(pad, 32);
+    return ld;
+}
 static inline int grid_for(int64_t count, int block, int cap) {
     int64_t g = (count + block - 1) / block;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
@@ -430,7 +438,7 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     c->kp = (int)(k <= 16 ? 16 : round_up(k, 32));
     c->kb = std::min(c->kp, 32);
     c->sm_count = prop.multiProcessorCount;
-    c->ldh = round_up(n_local, 32);
+    c->ldh = padded_ld(n_local);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t wbytes = (size_t)d * c->kp * sizeof(float), hbytes = (size_t)c->kp * c->ldh * sizeof(float);
     for (int i = 0; i < 2; ++i) {
@@ -545,11 +553,11 @@ static int data_changed(pymfb_ctx* c) {
 
 static int ensure_own_x(pymfb_ctx* c) {
     if (!c->X_own) {
-        c->ldx = round_up(c->n_loc, 32);
+        c->ldx = padded_ld(c->n_loc);
         CU(cudaMalloc(&c->X_own, (size_t)c->d * c->ldx * sizeof(float)));
         CU(cudaMemsetAsync(c->X_own, 0, (size_t)c->d * c->ldx * sizeof(float), c->stream));
     }
-    c->ldx = round_up(c->n_loc, 32);
+    c->ldx = padded_ld(c->n_loc);
     c->X = c->X_own;
     return 0;
 }
@@ -601,7 +609,7 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
         UP(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
     }
     unsigned hw = std::thread::hardware_concurrency();
-    const int nthr = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+    const int nthr = (int)std::max(1u, std::min(16u, hw ? hw : 1u));   // the pageable -> pinned copy is the slow leg (measured 10-20 GB/s vs 50 GB/s DMA)
     int64_t chunk = 0;
     for (int64_t r0 = 0; r0 < c->d; r0 += rows_per, ++chunk) {
         const int b = (int)(chunk % NB);
