@@ -247,9 +247,16 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     flops_alg = 4.0 * d * n_loc * k + 4.0 * n_loc * k * k + 4.0 * d * k * k
     t_stream_ms = t_h + t_x
     achieved = bytes_alg / (t_stream_ms * 1e-3) / 1e9 if t_stream_ms > 0 else 0.0
+    traffic = None
+    try:                                          # DRAM bytes per iteration of the two streaming kernels (ncu capture)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl_name)
+        if tj and world == 1 and path == "tc":
+            traffic = tj["h_update_bytes"] + tj["xht_bytes"]
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+        "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
         "kernel": "streaming pass = H-update kernel + X.H^T kernel (each reads X once per iteration)",
         "alg_bytes_per_iteration": bytes_alg, "h_update_ms": t_h, "xht_ms": t_x,
         "kernel_launches_timed": int(n_h + n_x),

@@ -29,6 +29,8 @@
 
 #include <cstdlib>
 #include <string>
+#include <vector>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -673,6 +675,19 @@ __device__ __forceinline__ void park_hilo(uint32_t taddr, const float (&v)[32]) 
     tmem_st32(taddr + 32, lo);
 }
 
+// PYMFB_TRACE (experiment builds only): CTA 0 records clock64() at the hand-over points of its first
+// TRACE_STAGES pipeline stages into dbg + 1 MB; dumped by tc_release() to $PYMFB_TRACE_FILE.
+#if defined(PYMFB_TRACE)
+constexpr int TRACE_STAGES = 4096;
+#define TRACE_AT(stage_idx, slot)                                                                           \
+    do {                                                                                                    \
+        if (dbg != nullptr && blockIdx.x == 0 && lane == 0 && (stage_idx) < (uint32_t)TRACE_STAGES)                   \
+            reinterpret_cast<long long*>(dbg + (1 << 18))[(size_t)(stage_idx) * 16 + (slot)] = clock64();   \
+    } while (0)
+#else
+#define TRACE_AT(stage_idx, slot) do { } while (0)
+#endif
+
 template <int KP>
 __global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
 k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
@@ -720,7 +735,9 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 const int col0 = tile * TILE_COLS;
                 for (int it = 0; it < nit; ++it) {
                     if (pcnt++ % NPROD == (uint32_t)warp) {
+                    TRACE_AT(pcnt - 1, 0);
                     mbar_wait(empty_bar(s), ph ^ 1);
+                    TRACE_AT(pcnt - 1, 1);
                     if (elect_one()) {
 #if defined(PYMFB_EXP_SKIP_WLOAD)
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES);
@@ -746,19 +763,22 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         {
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
-            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
+            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0; uint32_t mc = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
                     const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
                     const uint32_t b = g & 1u;
+                    TRACE_AT(mc, 8);
                     mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
                     bool first = true;
-                    for (; it < seg_end; ++it) {
+                    for (; it < seg_end; ++it, ++mc) {
+                        TRACE_AT(mc, 5);
                         mbar_wait(full_bar(s), ph);
                         mbar_wait(afull_bar(t), tph);
+                        TRACE_AT(mc, 6);
                         tc_fence_after();
                         const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
                         if (elect_one()) {
@@ -777,6 +797,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                             umma_commit(aempty_bar(t));
                         }
                         __syncwarp();
+                        TRACE_AT(mc, 7);
                         first = false;
                         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                         if (++t == Cfg::NT) { t = 0; tph ^= 1; }
@@ -792,11 +813,14 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         const int q = warp & 3;
         const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
-        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0;
+        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int it = 0; it < nit; ++it) {
+            for (int it = 0; it < nit; ++it, ++cc) {
+                if (q == 0) TRACE_AT(cc, 2);
                 mbar_wait(full_bar(s), ph);
+                if (q == 0) TRACE_AT(cc, 9);
                 mbar_wait(aempty_bar(t), tph ^ 1);
+                if (q == 0) TRACE_AT(cc, 3);
                 tc_fence_after();
 #if !defined(PYMFB_EXP_SKIP_CONVERT)
                 const float* xs = reinterpret_cast<const float*>(smem_gen + s * Cfg::STAGE_BYTES);
@@ -808,6 +832,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #endif
                 tc_fence_before();
                 __syncwarp();
+                if (q == 0) TRACE_AT(cc, 4);
                 if (lane == 0) mbar_arrive(afull_bar(t));
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 if (++t == Cfg::NT) { t = 0; tph ^= 1; }
@@ -830,7 +855,9 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
+                if (q == 0) TRACE_AT(g * SEG_STAGES, 10);
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                if (q == 0) TRACE_AT(g * SEG_STAGES, 11);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
@@ -847,6 +874,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (q == 0) TRACE_AT(g * SEG_STAGES, 12);
                 if (lane == 0) mbar_arrive(tempty_bar(b));
             }
             {
@@ -1230,7 +1258,25 @@ inline int tc_set_attrs() {
     return e == cudaSuccess ? 0 : 1;
 }
 
+#if defined(PYMFB_TRACE)
+inline void tc_trace_dump(TcPlan& p) {
+    const char* path = getenv("PYMFB_TRACE_FILE");
+    if (!p.dbg || !path) return;
+    const size_t n = (size_t)tc::TRACE_STAGES * 16;
+    std::vector<long long> h(n);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h.data(), p.dbg + (1 << 18), n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    FILE* f = fopen(path, "wb");
+    if (!f) return;
+    fwrite(h.data(), sizeof(long long), n, f);
+    fclose(f);
+}
+#endif
 inline void tc_release(TcPlan& p) {
+#if defined(PYMFB_TRACE)
+    tc_trace_dump(p);
+    if (p.dbg) { cudaFree(p.dbg); p.dbg = nullptr; }
+#endif
     if (p.Wsplit) cudaFree(p.Wsplit);
     if (p.Gsplit) cudaFree(p.Gsplit);
     for (int i = 0; i < 2; ++i) { if (p.Hs[i]) cudaFree(p.Hs[i]); p.Hs[i] = nullptr; p.hs_valid[i] = false; }
@@ -1270,6 +1316,13 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     }
     int rc = kp == 32 ? tc_set_attrs<32>() : kp == 64 ? tc_set_attrs<64>() : kp == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
     if (rc) { p.err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; return 1; }
+#if defined(PYMFB_TRACE)
+    {
+        const size_t bytes = (size_t)(1 << 18) * sizeof(float) + (size_t)tc::TRACE_STAGES * 16 * sizeof(long long);
+        if (cudaMalloc(&p.dbg, bytes) != cudaSuccess) { p.err = "cudaMalloc trace buffer failed"; return 1; }
+        cudaMemset(p.dbg, 0, bytes);
+    }
+#endif
     p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
     // X H^T tasks: (row block, column range); ~4 tasks per SM, each a multiple of 32 columns
     p.x_rb = (int)((d + 127) / 128);
