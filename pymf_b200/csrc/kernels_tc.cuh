@@ -1270,6 +1270,14 @@ inline void tc_trace_dump(TcPlan& p) {
     if (!f) return;
     fwrite(h.data(), sizeof(long long), n, f);
     fclose(f);
+    // fused-kernel event log (kernels_fused.cuh FTRACE): [count][(code, value, clock) ...]
+    std::vector<long long> ev((size_t)(2 << 20) / sizeof(long long));
+    if (cudaMemcpy(ev.data(), reinterpret_cast<char*>(p.dbg) + (2 << 20), (size_t)2 << 20, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    std::string p2 = std::string(path) + ".events";
+    f = fopen(p2.c_str(), "wb");
+    if (!f) return;
+    fwrite(ev.data(), sizeof(long long), ev.size(), f);
+    fclose(f);
 }
 #endif
 inline void tc_release(TcPlan& p) {
@@ -1318,7 +1326,7 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     if (rc) { p.err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; return 1; }
 #if defined(PYMFB_TRACE)
     {
-        const size_t bytes = (size_t)(1 << 18) * sizeof(float) + (size_t)tc::TRACE_STAGES * 16 * sizeof(long long);
+        const size_t bytes = (size_t)4 << 20;   // [0,1 MB) accumulator dumps | [1 MB, 1.5 MB) stage trace | [2 MB, 4 MB) fused-kernel event log
         if (cudaMalloc(&p.dbg, bytes) != cudaSuccess) { p.err = "cudaMalloc trace buffer failed"; return 1; }
         cudaMemset(p.dbg, 0, bytes);
     }

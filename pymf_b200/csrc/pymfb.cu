@@ -45,8 +45,29 @@ static int fail(const char* fmt, ...) {
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
         if (e_ != cudaSuccess)                                                                \
-            return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return fail("%s:%d %s -> %s%s", __FILE__, __LINE__, #call, cudaGetErrorString(e_), fault_note()); \
     } while (0)
+// Device-side watchdogs (bounded barrier / flag waits in the persistent kernels) leave a note in this mapped
+// host buffer before they trap, so that a protocol bug reads "which wait, which CTA" instead of only
+// "unspecified launch failure".  [0] = code (0 = none), [1] = CTA, [2] = aux, [3] = thread.
+static int* g_fault_host = nullptr;
+static int* g_fault_dev = nullptr;
+static int* fault_buffer() {
+    if (!g_fault_host) {
+        if (cudaHostAlloc((void**)&g_fault_host, 64 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); g_fault_host = nullptr; return nullptr; }
+        memset(g_fault_host, 0, 64 * sizeof(int));
+        if (cudaHostGetDevicePointer((void**)&g_fault_dev, g_fault_host, 0) != cudaSuccess) { cudaGetLastError(); g_fault_dev = nullptr; }
+    }
+    return g_fault_dev;
+}
+static const char* fault_note() {
+    static thread_local char buf[160];
+    buf[0] = 0;
+    if (g_fault_host && g_fault_host[0] != 0)
+        snprintf(buf, sizeof(buf), " [device watchdog: wait code %d, CTA %d, aux %d, thread %d]", g_fault_host[0], g_fault_host[1],
+                 g_fault_host[2], g_fault_host[3]);
+    return buf;
+}
 #define CK(call)                      \
     do {                              \
         int r_ = (call);              \
@@ -273,7 +294,7 @@ static int launch_fused(pymfb_ctx* c) {
     c->launches += 1;
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 0, &e0, &e1));
-    if (fused_launch(c->fused, c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->G, c->P, c->stream, &c->launches))
+    if (fused_launch(c->fused, c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->G, c->P, c->stream, &c->launches, fault_buffer()))
         return fail("fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CK(timing_end(c, 0, e0, e1));
     c->hcur ^= 1;

@@ -2,8 +2,9 @@
 
   python tests/_fused_sweep.py [d n k] > gpurun_out/fused_sweep.txt
 
-Prints ms/iteration and the fused-kernel time for each (sbc, slab, lag, hint); the first line is the
-two-pass baseline.  Parameters are read by fused_plan() from the environment at plan time.
+Prints ms/iteration and the fused-kernel time for each (depth, hint); the first line is the two-pass
+baseline.  Parameters are read by fused_plan() from the environment at plan time.  SWEEP="d,h;d,h"
+selects combinations, SWEEP=none prints only the baseline.
 """
 import itertools
 import os
@@ -39,22 +40,17 @@ def main():
     grid = os.environ.get("SWEEP", "full")
     if grid == "none":
         return
-    if grid == "full":
-        combos = [(sbc, slab, bcols, lag, 1)
-                  for sbc, slab, bcols in ((1024, 256, 256), (1024, 256, 128), (1024, 512, 256), (512, 256, 256),
-                                           (512, 256, 128), (2048, 256, 256), (2048, 512, 512), (512, 512, 128))
-                  for lag in (1, 2, 3, 4)]
-    else:
-        combos = [tuple(int(x) for x in c.split(",")) for c in grid.split(";")]
-    for sbc, slab, bcols, lag, hint in combos:
-        env = {"PYMFB_FUSED": "1", "PYMFB_FUSED_SBC": str(sbc), "PYMFB_FUSED_SLAB": str(slab),
-               "PYMFB_FUSED_BCOLS": str(bcols), "PYMFB_FUSED_LAG": str(lag), "PYMFB_FUSED_HINT": str(hint)}
+    combos = ([(2, 1), (1, 1), (3, 1), (4, 1), (2, 0), (3, 0)] if grid == "full"
+              else [tuple(int(x) for x in c.split(",")) for c in grid.split(";")])
+    for combo in combos:
+        depth, hint = combo[0], combo[1]
+        pf = combo[2] if len(combo) > 2 else 1
+        env = {"PYMFB_FUSED": "1", "PYMFB_FUSED_DEPTH": str(depth), "PYMFB_FUSED_HINT": str(hint), "PYMFB_FUSED_PF": str(pf)}
         try:
             ms, t0, t1, f = run(d, n, k, env)
-            print("sbc %4d slab %3d bcols %4d lag %2d hint %d  window %5.1f MB  ms/iter %.3f  fused %.3f  ferr %.4f"
-                  % (sbc, slab, bcols, lag, hint, (lag + 1) * d * sbc * 4 / 1e6, ms, t0, f), flush=True)
+            print("fused depth %d hint %d pf %d  ms/iter %.3f  fused(+gh) %.3f  ferr %.4f" % (depth, hint, pf, ms, t0, f), flush=True)
         except Exception as e:  # noqa: BLE001
-            print("sbc %d slab %d bcols %d lag %d hint %d FAILED: %s" % (sbc, slab, bcols, lag, hint, e), flush=True)
+            print("fused depth %d hint %d FAILED: %s" % (depth, hint, e), flush=True)
             break
 
 
