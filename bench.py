@@ -35,6 +35,12 @@ WORKLOADS = {
     "cfg2": (4096, 262144, 32, "cfg2: 4096x262144 fp32, k=32"),
     "cfg3": (16384, 1048576, 128, "cfg3: 16384x1M fp32, k=128 (STRONG: columns split over GPUs)"),
     "cfg4k64": (8192, 524288, 64, "cfg4: 8192x524288, k=64"),
+    "cfg4k16": (8192, 524288, 16, "cfg4: 8192x524288, k=16"),
+    "cfg4k32": (8192, 524288, 32, "cfg4: 8192x524288, k=32"),
+    "cfg4k128": (8192, 524288, 128, "cfg4: 8192x524288, k=128"),
+    "cfg4k256": (8192, 524288, 256, "cfg4: 8192x524288, k=256"),
+    "cfg4k512": (8192, 524288, 512, "cfg4: 8192x524288, k=512"),
+    "cfg5": (32768, 524288, 64, "cfg5: 32768x524288 per GPU (64 GiB), k=64, weak scaling"),
 }
 METRIC = "NMF MU iterations/sec"
 UNIT = "iterations/s"
