@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(HCfg<KP>::THREADS, 1)
 k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
-              float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg) {
+              float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
+              int kh_rows) {
+    // kh_rows: rows of H contracted for G H (= the padded k of the whole problem).  For k <= 128 it equals KP;
+    // for k > 128 the launch handles one 128-wide block of bases: mapH spans all kh_rows rows of H, mapG is the
+    // block's [G_hi | G_lo] column slice, and Hc / Hn / Hs point at the block's rows.
     using Cfg = HCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -255,7 +259,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_gen;
 
     const int nd = (d + R1 - 1) / R1;            // stages over the rows of X
-    const int nit = nd + KP / R1;                // + stages over the rows of H (for G H)
+    const int nit = nd + kh_rows / R1;           // + stages over the rows of H (for G H)
     auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
     auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
@@ -438,7 +442,8 @@ template <int KP>
 __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
-         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg) {
+         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp) {
+    // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
     using Cfg = XCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -592,7 +597,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 for (int j = 0; j < Cfg::NJ; ++j) o[j] = areg[j];
             }
             if (row < d) {
-                float* dst = P + (int64_t)row * KP + jbase;
+                float* dst = P + (int64_t)row * ldp + jbase;
 #pragma unroll
                 for (int j = 0; j < Cfg::NJ; ++j) atomicAdd(dst + j, areg[j]);
             }
@@ -1130,34 +1135,34 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
-// H (kp x ldh) -> Hs = [H_hi rows ; H_lo rows] (2kp x ldh); used when the X.H^T pass runs on an H that
-// did not come out of the H-update epilogue (bootstrap, user-assigned H).
-__global__ void k_split_rows(const DevState* __restrict__ st, const float* __restrict__ H, int kp, int64_t ldh,
+// Rows [row0, row0 + kpb) of H (.. x ldh) -> chunk-major Hs = [H_hi rows ; H_lo rows] of that block; used when
+// the X.H^T pass runs on an H that did not come out of the H-update epilogue (bootstrap, user-assigned H).
+__global__ void k_split_rows(const DevState* __restrict__ st, const float* __restrict__ H, int kpb, int64_t ldh,
                              float* __restrict__ Hs) {
     if (st->stop) return;
-    const int64_t total = (int64_t)kp * ldh;
+    const int64_t total = (int64_t)kpb * ldh;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / ldh);
         const int64_t c = i - (int64_t)r * ldh;
         const float v = H[i];
         const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        Hs[hs_index(r, c, 2 * kp)] = hi;
-        Hs[hs_index(kp + r, c, 2 * kp)] = v - hi;
+        Hs[hs_index(r, c, 2 * kpb)] = hi;
+        Hs[hs_index(kpb + r, c, 2 * kpb)] = v - hi;
     }
 }
 
-// [hi | lo] split of a small row-major matrix: src rows x kp -> dst rows x 2kp   (W and G)
-__global__ void k_split_hilo(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int kp,
-                             float* __restrict__ dst) {
+// [hi | lo] split of columns [col0, col0 + kpb) of a row-major matrix (rows x ld): -> dst rows x 2 kpb   (W and G)
+__global__ void k_split_hilo(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int ld,
+                             int col0, int kpb, float* __restrict__ dst) {
     if (st->stop) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * kp) return;
-    const int64_t r = i / kp;
-    const int c = (int)(i % kp);
-    const float v = src[i];
+    if (i >= rows * kpb) return;
+    const int64_t r = i / kpb;
+    const int c = (int)(i % kpb);
+    const float v = src[r * ld + col0 + c];
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    dst[r * 2 * kp + c] = hi;
-    dst[r * 2 * kp + kp + c] = v - hi;
+    dst[r * 2 * kpb + c] = hi;
+    dst[r * 2 * kpb + kpb + c] = v - hi;
 }
 
 }  // namespace tc
@@ -1174,8 +1179,12 @@ struct TcPlan {
     const float* Hbuf[2] = {nullptr, nullptr};
     float* Hs[2] = {nullptr, nullptr};        // [H_hi ; H_lo] companion of each H buffer, chunk-major (hs_index)
     bool hs_valid[2] = {false, false};
-    float* Wsplit = nullptr;   // d x 2kp  [W_hi | W_lo]
-    float* Gsplit = nullptr;   // kp x 2kp [G_hi | G_lo]
+    // k > 128 runs as nblk = kp / 128 blocks of kpb = 128 bases (one launch of each pass per block, each streaming
+    // X); k <= 128: nblk = 1, kpb = kp.  All per-block buffers are slices of the allocations below.
+    int nblk = 1, kpb = 0;
+    float* Wsplit = nullptr;   // nblk x (d x 2kpb)   [W_hi | W_lo] of each block of bases
+    float* Gsplit = nullptr;   // nblk x (kp x 2kpb)  [G_hi | G_lo] column slice of each block, all kp rows
+    CUtensorMap mapW_b[4], mapG_b[4], mapH_xb[2][4];   // per-block maps (k > 128)
     CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
     CUtensorMap mapX_p, mapH_p[2];   // TS kernels: plain (unswizzled) 128-column x 32-row boxes
     CUtensorMap mapH_a[2];           // H as the A operand of the H.H^T tasks (128-row boxes, rows >= kp zero-filled)
@@ -1235,7 +1244,7 @@ inline bool make_map_plain(CUtensorMap* m, const float* base, int64_t rows, int6
 }
 
 inline bool tc_supported(int64_t d, int64_t n_loc, int kp, int64_t ldx, const float* X, std::string* why) {
-    if (kp % 32 != 0 || kp < 32 || kp > 128) { *why = "k (padded) must be 32..128 in steps of 32"; return false; }
+    if (kp % 32 != 0 || kp < 32 || (kp > 128 && (kp % 128 != 0 || kp > 512))) { *why = "k (padded) must be 32..128 in steps of 32, or 256 / 384 / 512"; return false; }
     if (ldx % 4 != 0 || ((uintptr_t)X & 15) != 0) { *why = "X must be 16-byte aligned with ld % 4 == 0"; return false; }
     if (d >= (1LL << 31) || n_loc >= (1LL << 31) - 256) { *why = "dimension too large"; return false; }
     if (d < 64 || n_loc < 128) { *why = "problem too small for the tensor-core tiles"; return false; }
@@ -1297,6 +1306,8 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     tc_release(p);
     p.device = device; p.sm_count = sm_count; p.d = d; p.n_loc = n_loc; p.k = k; p.kp = kp; p.X = X; p.ldx = ldx; p.ldh = ldh;
     p.Hbuf[0] = H0; p.Hbuf[1] = H1;
+    p.nblk = kp > 128 ? kp / 128 : 1;
+    p.kpb = kp > 128 ? 128 : kp;
     if (cudaMalloc(&p.Wsplit, (size_t)d * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Wsplit failed"; return 1; }
     if (cudaMalloc(&p.Gsplit, (size_t)kp * 2 * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc Gsplit failed"; return 1; }
     for (int i = 0; i < 2; ++i) {
@@ -1307,11 +1318,17 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     bool ok = true;
     ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, true, &p.err);
     ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, false, &p.err);
-    ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * kp, 2 * kp, tc::R1, true, &p.err);
-    ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * kp, 2 * kp, tc::R1, true, &p.err);
+    ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
+    ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
+    for (int b = 0; b < p.nblk; ++b) {
+        ok = ok && make_map(&p.mapW_b[b], p.Wsplit + (size_t)b * d * 2 * p.kpb, d, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
+        ok = ok && make_map(&p.mapG_b[b], p.Gsplit + (size_t)b * kp * 2 * p.kpb, kp, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
+        for (int i = 0; i < 2; ++i)
+            ok = ok && make_map(&p.mapH_xb[i][b], p.Hs[i] + (size_t)b * 2 * p.kpb * ldh, (ldh / 32) * 2 * p.kpb, 32, 32, 2 * p.kpb, false, &p.err);
+    }
     for (int i = 0; i < 2; ++i) {
         ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
-        ok = ok && make_map(&p.mapH_x[i], p.Hs[i], (ldh / 32) * 2 * kp, 32, 32, 2 * kp, false, &p.err);   // [H_hi ; H_lo] chunks as B
+        ok = ok && make_map(&p.mapH_x[i], p.Hs[i], (ldh / 32) * 2 * p.kpb, 32, 32, 2 * p.kpb, false, &p.err);   // [H_hi ; H_lo] chunks as B (block 0)
         ok = ok && make_map(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 128, false, &p.err);        // H as A
     }
     ok = ok && make_map_plain(&p.mapX_p, X, d, n_loc, ldx, tc::TILE_COLS, tc::R1, &p.err);
@@ -1322,7 +1339,7 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         p.use_ts = kp <= 64 && !(force_ss && force_ss[0] == '1');
         if (p.use_ts && (kp == 32 ? ts_set_attrs<32>() : ts_set_attrs<64>())) { p.err = "cudaFuncSetAttribute (TS kernels) failed"; return 1; }
     }
-    int rc = kp == 32 ? tc_set_attrs<32>() : kp == 64 ? tc_set_attrs<64>() : kp == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
+    int rc = p.kpb == 32 ? tc_set_attrs<32>() : p.kpb == 64 ? tc_set_attrs<64>() : p.kpb == 96 ? tc_set_attrs<96>() : tc_set_attrs<128>();
     if (rc) { p.err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; return 1; }
 #if defined(PYMFB_TRACE)
     {
@@ -1368,18 +1385,24 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
 
 // refresh [W_hi | W_lo] and [G_hi | G_lo] after W / G changed
 inline int tc_after_gram(TcPlan& p, const DevState* st, const float* W, const float* G, cudaStream_t stream, int64_t* launches) {
-    const int64_t nw = p.d * p.kp, ng = (int64_t)p.kp * p.kp;
-    tc::k_split_hilo<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(st, W, p.d, p.kp, p.Wsplit);
-    tc::k_split_hilo<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(st, G, p.kp, p.kp, p.Gsplit);
-    *launches += 2;
+    const int64_t nw = p.d * p.kpb, ng = (int64_t)p.kp * p.kpb;
+    for (int b = 0; b < p.nblk; ++b) {
+        tc::k_split_hilo<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(st, W, p.d, p.kp, b * p.kpb, p.kpb, p.Wsplit + (size_t)b * p.d * 2 * p.kpb);
+        tc::k_split_hilo<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(st, G, p.kp, p.kp, b * p.kpb, p.kpb, p.Gsplit + (size_t)b * p.kp * 2 * p.kpb);
+    }
+    *launches += 2 * p.nblk;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 template <int KP>
 inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = std::min(p.h_tiles, p.sm_count);
-    tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_h, p.mapW, p.mapH_h[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg);
+    for (int b = 0; b < p.nblk; ++b) {        // one launch per block of <= 128 bases (k <= 128: one launch)
+        const size_t hoff = (size_t)b * p.kpb * p.ldh;
+        tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
+            p.mapX_h, p.mapW_b[b], p.mapH_h[hsrc], p.mapG_b[b], st, p.Hbuf[hsrc] + hoff, Hn + hoff, p.Hs[hsrc ^ 1] + 2 * hoff,
+            p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp);
+    }
 }
 template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
@@ -1403,29 +1426,45 @@ inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn
         *launches += 1;
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
-    switch (p.kp) {
+    switch (p.kpb) {
         case 32: tc_launch_h<32>(p, st, hsrc, Hn, stream); break;
         case 64: tc_launch_h<64>(p, st, hsrc, Hn, stream); break;
         case 96: tc_launch_h<96>(p, st, hsrc, Hn, stream); break;
         default: tc_launch_h<128>(p, st, hsrc, Hn, stream); break;
     }
-    *launches += 1;
+    *launches += p.nblk;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 template <int KP>
 inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
     const int grid = std::min(p.x_tasks, p.sm_count);
-    tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_x, p.mapH_x[hsrc], st, P, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks, p.dbg);
+    for (int b = 0; b < p.nblk; ++b)
+        tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
+            p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
+            p.dbg, p.kp);
 }
-// true when the launch also produced H H^T (so the caller skips its own H H^T kernel)
-inline bool tc_xht_includes_hht(const TcPlan& p) { return p.use_ts; }
+// true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
+// extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
+inline bool tc_xht_includes_hht(const TcPlan& p) { return true; }
+// H H^T on the SS kernels: the X.H^T kernel with X := H (kp rows, 128-row boxes zero-filled beyond kp)
+template <int KP>
+inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cudaStream_t stream) {
+    const int hh_rb = (p.kp + 127) / 128;
+    const int ntasks = p.hh_tasks * hh_rb;
+    const int grid = std::min(ntasks, p.sm_count);
+    for (int b = 0; b < p.nblk; ++b)
+        tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
+            p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
+            nullptr, p.kp);
+}
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
     if (!p.hs_valid[hsrc]) {
-        tc::k_split_rows<<<4 * p.sm_count, 256, 0, stream>>>(st, Hc, p.kp, p.ldh, p.Hs[hsrc]);
-        *launches += 1;
+        for (int b = 0; b < p.nblk; ++b)
+            tc::k_split_rows<<<4 * p.sm_count, 256, 0, stream>>>(st, Hc + (size_t)b * p.kpb * p.ldh, p.kpb, p.ldh,
+                                                                p.Hs[hsrc] + (size_t)b * 2 * p.kpb * p.ldh);
+        *launches += p.nblk;
         p.hs_valid[hsrc] = true;
     }
     if (p.use_ts) {
@@ -1433,13 +1472,20 @@ inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cuda
         *launches += 1;
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
-    switch (p.kp) {
+    switch (p.kpb) {
         case 32: tc_launch_x<32>(p, st, hsrc, P, stream); break;
         case 64: tc_launch_x<64>(p, st, hsrc, P, stream); break;
         case 96: tc_launch_x<96>(p, st, hsrc, P, stream); break;
         default: tc_launch_x<128>(p, st, hsrc, P, stream); break;
     }
-    *launches += 1;
+    float* PB = P + p.d * p.kp;
+    switch (p.kpb) {
+        case 32: tc_launch_hht<32>(p, st, hsrc, PB, stream); break;
+        case 64: tc_launch_hht<64>(p, st, hsrc, PB, stream); break;
+        case 96: tc_launch_hht<96>(p, st, hsrc, PB, stream); break;
+        default: tc_launch_hht<128>(p, st, hsrc, PB, stream); break;
+    }
+    *launches += 2 * p.nblk;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -461,6 +461,8 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     // tcgen05 path (kp % 32 == 0) serves it: 8192 x 524288, k = 16 ran 15.2 ms / iteration on SIMT vs 6.1 ms padded.
     const bool streaming_size = (double)d * (double)n_local >= 16777216.0 && d >= 64 && n_local >= 128;
     c->kp = (int)((k <= 16 && !streaming_size) ? 16 : round_up(k, 32));
+    // 128 < k <= 512 on a streaming-sized problem: blocks of 128 bases on the tensor path (kernels_tc.cuh)
+    if (k > 128 && k <= 512 && streaming_size) c->kp = (int)round_up(k, 128);
     c->kb = std::min(c->kp, 32);
     c->sm_count = prop.multiProcessorCount;
     c->ldh = padded_ld(n_local);

@@ -213,11 +213,36 @@ def test_large_shape_properties():
         e.close()
 
 
+@pytest.mark.parametrize("shape", [(4096, 262144, 32), (8192, 131072, 64), (16384, 65536, 128)])
+def test_full_size_properties(shape):
+    """BASELINE-sized shards (cfg2 in full; cfg4 / cfg3 at their d and k on a 4 GiB column shard), data
+    generated on the device: Lee-Seung monotonicity, non-negativity, and the trace-identity error of
+    the tensor-core path against the direct fp32/fp64 residual pass sqrt(sum((X - W H)^2))."""
+    d, n, k = shape
+    e = pymf_b200.Engine(d, n, k)
+    try:
+        e.set_err_mode("trace")
+        e.gen_x(77); e.gen_w(78); e.gen_h(79)
+        ferr, done = e.run(6, early_stop=False)
+        assert e.active_path == "tc"
+        assert done == 6 and np.all(np.isfinite(ferr))
+        assert np.all(np.diff(ferr) <= 1e-5 * ferr[:-1])
+        e.set_err_mode("direct")
+        direct = e.frobenius()
+        assert abs(direct - ferr[-1]) / direct < TOL_FERR, (direct, ferr[-1])
+        W = e.get_w(np.float32)
+        assert W.min() >= 0 and np.isfinite(W).all()
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("shape", [(256, 512, 32), (300, 1000, 40), (512, 640, 128), (1024, 4096, 64),
-                                   (4096, 2048, 32), (200, 3000, 96), (130, 131, 17)])
+                                   (4096, 2048, 32), (200, 3000, 96), (130, 131, 17),
+                                   (2048, 8192, 256), (2048, 8200, 200), (4096, 4100, 16), (1024, 16384, 512)])
 def test_tensor_core_path_matches_fp32_path(shape):
     """tcgen05 3xTF32 kernels vs the fp32 CUDA-core kernels vs the float64 oracle, 3 iterations,
-    including shapes whose d / n / k are not multiples of the tile sizes."""
+    including shapes whose d / n / k are not multiples of the tile sizes, k <= 16 padded to 32 and
+    128 < k <= 512 run as blocks of 128 bases (both only on streaming-sized problems, d*n >= 2^24)."""
     d, n, k = shape
     rng = np.random.RandomState(d + n + k)
     X = rng.random_sample((d, n)).astype(np.float32)
