@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.002)
 
     def finish(self):
         self._stop_evt.set()
@@ -276,9 +276,17 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     e2e = None
     if not args.no_e2e:
         rng = np.random.default_rng(1234 + rank)
-        Xh = rng.random((d, n_loc), dtype=np.float32)
-        W0 = rng.random((d, k))
-        H0 = rng.random((k, n_loc))
+        if args.e2e_source == "pinned":          # page-locked host buffers (the contract's e2e source)
+            Xh = pymf_b200.pinned_empty((d, n_loc), np.float32)
+            W0 = pymf_b200.pinned_empty((d, k), np.float64)
+            H0 = pymf_b200.pinned_empty((k, n_loc), np.float64)
+            rng.random(out=Xh, dtype=np.float32)
+            rng.random(out=W0)
+            rng.random(out=H0)
+        else:                                    # ordinary pageable numpy arrays
+            Xh = rng.random((d, n_loc), dtype=np.float32)
+            W0 = rng.random((d, k))
+            H0 = rng.random((k, n_loc))
         m = pymf_b200.NMF(Xh, num_bases=k, device=local_rank, path=args.path,
                           process_group=(True if world > 1 else None))
         barrier()
@@ -297,6 +305,7 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
         e2e = {"value": units_per_step * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "seconds_total": t_e2e,
                "seconds_upload": t1 - t0, "seconds_iterations": t2 - t1, "seconds_download": t3 - t2,
+               "host_source": args.e2e_source, "x_upload_direct_dma": bool(m._engine.last_upload_pinned),
                "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download" % steps}
         del m
 
@@ -335,6 +344,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default=None, choices=[None, "auto", "simt", "tc"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-source", default="pinned", choices=["pinned", "pageable"],
+                    help="host memory the e2e leg reads X/W/H from (default: page-locked)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     d, n, k, desc = WORKLOADS[args.workload]

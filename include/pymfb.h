@@ -20,6 +20,7 @@
 #ifndef PYMFB_H
 #define PYMFB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -72,6 +73,19 @@ int pymfb_destroy(pymfb_ctx* ctx);
 int pymfb_set_option(pymfb_ctx* ctx, int option, int64_t value);
 
 /*
+ * BNMF penalty - the binary-factor variant of the same loop (pymf/bnmf.py:22-123, a subclass
+ * that overrides update_w / update_h only).  With lamb > 0 the update kernels' ratio epilogue
+ * becomes   H <- H * (W^T X + 3 lamb_h H^2) / (G H + 2 lamb_h H^3 + lamb_h H + 1e-9)   (:79-82)
+ *           W <- W * (X H^T + 3 lamb_w W^2) / (W B + 2 lamb_w W^3 + lamb_w W + 1e-9)   (:87-90)
+ * and after every H update lamb_w *= increase_w, lamb_h *= increase_h (:84-85; BNMF.factorize
+ * starts both at 1/niter, :117-118, with _LAMB_INCREASE_W/H = 1.1, :75-76).  lamb = 0 (the
+ * default) is plain NMF, bit-identical to not calling this.  get_penalty returns the current
+ * weights (the reference's _lamb_W / _lamb_H after factorize).
+ */
+int pymfb_set_penalty(pymfb_ctx* ctx, double lamb_w, double lamb_h, double increase_w, double increase_h);
+int pymfb_get_penalty(pymfb_ctx* ctx, double* lamb_w, double* lamb_h);
+
+/*
  * Multi-GPU (one process per GPU).  Rank 0 calls pymfb_comm_unique_id (128 bytes, an
  * ncclUniqueId), the host layer broadcasts it, every rank calls pymfb_comm_init.
  * After that pymfb_prepare / pymfb_run sum the packed [X H^T | H H^T] partials (and
@@ -94,6 +108,20 @@ int pymfb_comm_init(pymfb_ctx* ctx, const void* uid128, int world, int rank);
 int pymfb_bind_x(pymfb_ctx* ctx, const float* x_dev, int64_t ld);
 int pymfb_upload_x(pymfb_ctx* ctx, const void* x_host, int dtype, int64_t ld);
 int pymfb_gen_x(pymfb_ctx* ctx, uint64_t seed);
+
+/*
+ * Ingest fast path (the step before the hot path).  pymfb_upload_x looks at
+ * its source pointer: PAGE-LOCKED host memory (pymfb_host_alloc, cudaHostAlloc/Register, torch
+ * pin_memory) is read by the copy engines directly - fp32 in one strided DMA into X, fp64 in
+ * row chunks through a device staging pair with the fp64->fp32 cast overlapped - with no
+ * host-side copy; pageable memory goes through the pinned staging ring filled by host threads.
+ * pymfb_last_upload_pinned tells which one the last upload took (1 = direct DMA).
+ * pymfb_host_alloc / pymfb_host_free hand out page-locked buffers for callers that build X in
+ * place (numpy arrays are wrapped around them by pymf_b200.pinned_empty).
+ */
+int pymfb_host_alloc(void** out, size_t bytes);
+int pymfb_host_free(void* ptr);
+int pymfb_last_upload_pinned(pymfb_ctx* ctx);
 
 /*
  * Factor access - the .W / .H attributes (pymf/nmf.py:42-43,116-120,173-177).

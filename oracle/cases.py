@@ -38,10 +38,27 @@ CASES = {
 }
 
 
+# BNMF parity cases (pymf/bnmf.py).  kind "bin": X is a planted BINARY matrix (W* H* > 0 with sparse
+# binary factors, the data BNMF is made for); W0/H0 ~ U[0,1) from the same numpy stream.
+BNMF_CASES = {
+    "bnmf_bin": dict(kind="bin", seed=21, d=64, n=200, k=6, niter=30, keep=[1, 10, 30]),
+    "bnmf_ragged": dict(kind="np", seed=23, d=37, n=201, k=5, niter=20, keep=[1, 20]),
+    "bnmf_tc": dict(kind="hash", seed=55, d=512, n=640, k=32, niter=12, keep=[1, 12], store32=True),
+    "bnmf_k40": dict(kind="hash", seed=57, d=300, n=1000, k=40, niter=10, keep=[1, 10], store32=True),
+}
+
+
 def build(name):
-    c = CASES[name]
+    c = CASES[name] if name in CASES else BNMF_CASES[name]
     d, n, k = c["d"], c["n"], c["k"]
-    if c["kind"] == "np":
+    if c["kind"] == "bin":
+        np.random.seed(c["seed"])
+        Ws = (np.random.random((d, k)) < 0.3).astype(np.float64)
+        Hs = (np.random.random((k, n)) < 0.3).astype(np.float64)
+        X = (Ws.dot(Hs) > 0).astype(np.float64)
+        W0 = np.random.random((d, k))
+        H0 = np.random.random((k, n))
+    elif c["kind"] == "np":
         np.random.seed(c["seed"])
         X = np.random.random((d, n))
         W0 = np.random.random((d, k))

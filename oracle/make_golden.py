@@ -14,7 +14,7 @@ import sys
 import numpy as np
 
 from . import cases
-from .ref_loader import load_reference_nmf
+from .ref_loader import load_reference_bnmf, load_reference_nmf
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -85,5 +85,44 @@ def main():
         print(name, "ferr", ferr[0], "->", ferr[-1])
 
 
+def main_bnmf():
+    """BNMF fixtures: the reference's hooks stepped exactly as NMF.factorize steps them
+    (pymf/nmf.py:182-190) after BNMF.factorize's lamb initialisation (pymf/bnmf.py:117-118), plus one
+    whole factorize() call per case for the end state / ferr vector / final lamb."""
+    refb = load_reference_bnmf()
+    if refb is None:
+        sys.exit("no reference checkout found (set PYMF_REF)")
+    for name, c in cases.BNMF_CASES.items():
+        X, W0, H0 = cases.build(name)
+        X = X.astype(np.float64)
+        niter, keep = c["niter"], set(c["keep"])
+        m = refb.BNMF(X, num_bases=c["k"])
+        m.W, m.H = W0.copy(), H0.copy()
+        m._lamb_W = m._lamb_H = 1.0 / niter
+        ferr = np.zeros(niter)
+        snaps = {}
+        for i in range(niter):
+            m.update_w()
+            m.update_h()
+            ferr[i] = m.frobenius_norm()
+            if (i + 1) in keep:
+                snaps["W_%d" % (i + 1)] = m.W.copy()
+                snaps["H_%d" % (i + 1)] = m.H.copy()
+        lam_steps = np.array([m._lamb_W, m._lamb_H])
+        f = refb.BNMF(X, num_bases=c["k"])
+        f.W, f.H = W0.copy(), H0.copy()
+        f.factorize(niter=niter)
+        whole = {"Wf": f.W.copy(), "Hf": f.H.copy()}
+        if c.get("store32", False):
+            snaps = {k_: v.astype(np.float32) for k_, v in snaps.items()}
+            whole = {k_: v.astype(np.float32) for k_, v in whole.items()}
+        np.savez(os.path.join(OUT, "%s.npz" % name), ferr=ferr, lam_steps=lam_steps, ferr_whole=f.ferr.copy(),
+                 lam_whole=np.array([f._lamb_W, f._lamb_H]), **snaps, **whole)
+        print(name, "ferr", ferr[0], "->", ferr[-1], "len(ferr_whole)", len(f.ferr), "lam", f._lamb_H)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bnmf":
+        main_bnmf()
+        sys.exit(0)
     main()

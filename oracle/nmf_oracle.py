@@ -82,6 +82,57 @@ def factorize(X, W, H, niter=1, compute_w=True, compute_h=True, compute_err=True
 
 
 # --------------------------------------------------------------------------
+# BNMF (pymf/bnmf.py): the same loop with a penalty that drives W and H towards {0, 1}.
+# Pinned like the NMF functions: tests/golden/bnmf_*.npz come from the unmodified reference.
+# --------------------------------------------------------------------------
+LAMB_INCREASE_W = 1.1         # pymf/bnmf.py:75
+LAMB_INCREASE_H = 1.1         # pymf/bnmf.py:76
+
+
+def bnmf_update_h(X, W, H, lam):
+    """In-place BNMF H update; lam = {"W": lamb_W, "H": lamb_H} grows here.  pymf/bnmf.py:78-85."""
+    H1 = np.dot(W.T, X) + 3.0 * lam["H"] * (H ** 2)                                         # :79
+    H2 = np.dot(np.dot(W.T, W), H) + 2 * lam["H"] * (H ** 3) + lam["H"] * H + EPS_DENOM     # :80
+    H *= H1 / H2                                                                            # :81
+    lam["W"] = LAMB_INCREASE_W * lam["W"]                                                   # :83
+    lam["H"] = LAMB_INCREASE_H * lam["H"]                                                   # :84
+    return H
+
+
+def bnmf_update_w(X, W, H, lam):
+    """In-place BNMF W update.  pymf/bnmf.py:86-89."""
+    W1 = np.dot(X, H.T) + 3.0 * lam["W"] * (W ** 2)                                         # :87
+    W2 = np.dot(W, np.dot(H, H.T)) + 2.0 * lam["W"] * (W ** 3) + lam["W"] * W + EPS_DENOM   # :88
+    W *= W1 / W2                                                                            # :89
+    return W
+
+
+def bnmf_factorize(X, W, H, niter=10, compute_w=True, compute_h=True, compute_err=True,
+                   early_stop=True, record=None, lam=None):
+    """pymf/bnmf.py:91-123: lamb_W = lamb_H = 1/niter, then NMF.factorize's loop
+    (pymf/nmf.py:182-202) over the overridden hooks.  Returns ferr (or None); the final
+    penalty weights are left in ``lam`` when a dict is passed."""
+    lam = {} if lam is None else lam
+    lam["W"] = 1.0 / niter                                 # :117
+    lam["H"] = 1.0 / niter                                 # :118
+    ferr = np.zeros(niter) if compute_err else None
+    for i in range(niter):
+        if compute_w:
+            bnmf_update_w(X, W, H, lam)
+        if compute_h:
+            bnmf_update_h(X, W, H, lam)
+        if compute_err:
+            ferr[i] = frobenius_norm(X, W, H)
+        if record is not None:
+            record(i, W, H, ferr[i] if compute_err else None)
+        if early_stop and i > 1 and compute_err:
+            if converged(ferr, i, X.shape[1]):
+                ferr = ferr[:i]
+                break
+    return ferr
+
+
+# --------------------------------------------------------------------------
 # Synthetic inputs shared by tests, smoke() and bench.py (SURVEY.md section 8d).
 # The device generator in pymf_b200/csrc/pymfb.cu (k_gen_uniform) implements the
 # same integer hash so that any shard / tile regenerates bit-identically.

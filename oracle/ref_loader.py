@@ -30,3 +30,26 @@ def load_reference_nmf():
     mod.xrange = range                       # the file's only py2-ism
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_bnmf():
+    """Returns the reference's pymf/bnmf.py module (with .BNMF) or None.  bnmf.py does
+    ``from .nmf import NMF`` (:18), so it is loaded as a submodule of a synthetic, empty
+    package whose ``nmf`` member is the by-path module above - pymf/__init__.py (which
+    needs cvxopt) is never executed, and nothing is copied or edited."""
+    import sys
+    import types
+    nmf = load_reference_nmf()
+    if nmf is None:
+        return None
+    pkg_name = "_pymf_ref_pkg"
+    pkg_dir = os.path.dirname(find_reference())
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = [pkg_dir]
+    sys.modules[pkg_name] = pkg
+    sys.modules[pkg_name + ".nmf"] = nmf
+    spec = importlib.util.spec_from_file_location(pkg_name + ".bnmf", os.path.join(pkg_dir, "bnmf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[pkg_name + ".bnmf"] = mod
+    spec.loader.exec_module(mod)
+    return mod

@@ -3,6 +3,6 @@
 Only the NMF multiplicative-update path of the reference package is provided
 (pymf/__init__.py:16-43 re-exports ~20 other factorizations - out of scope).
 """
-from pymf_b200 import NMF  # noqa: F401
+from pymf_b200 import NMF, BNMF  # noqa: F401
 
-__all__ = ["NMF"]
+__all__ = ["NMF", "BNMF"]

@@ -30,11 +30,16 @@ SIGNATURES = {
     "pymfb_create": (C.c_int, [C.POINTER(_c_ctx), C.c_int, _i64, _i64, _i64, _i64, C.c_int]),
     "pymfb_destroy": (C.c_int, [_c_ctx]),
     "pymfb_set_option": (C.c_int, [_c_ctx, C.c_int, _i64]),
+    "pymfb_set_penalty": (C.c_int, [_c_ctx, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "pymfb_get_penalty": (C.c_int, [_c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pymfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pymfb_comm_init": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int]),
     "pymfb_bind_x": (C.c_int, [_c_ctx, C.c_void_p, _i64]),
     "pymfb_upload_x": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, _i64]),
     "pymfb_gen_x": (C.c_int, [_c_ctx, C.c_uint64]),
+    "pymfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "pymfb_host_free": (C.c_int, [C.c_void_p]),
+    "pymfb_last_upload_pinned": (C.c_int, [_c_ctx]),
     "pymfb_set_w": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),
     "pymfb_set_h": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),
     "pymfb_get_w": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),

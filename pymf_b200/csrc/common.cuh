@@ -25,6 +25,16 @@ struct DevState {
     unsigned pad_;
 };
 
+// The multiplicative ratio shared by every update kernel.  num = W^T X (or X H^T), den = G H (or W B).
+//   lam == 0 : NMF   v * num / (den + 1e-9)                                        pymf/nmf.py:124-126, 130-132
+//   lam != 0 : BNMF  v * ((num + 3 lam v^2) / (den + 2 lam v^3 + lam v + 1e-9))    pymf/bnmf.py:79-82, 87-90
+// (lam is uniform over the launch, so the branch does not diverge; lam == 0 keeps NMF bit-identical.)
+__device__ __forceinline__ float mu_ratio(float v, float num, float den, float lam) {
+    if (lam == 0.f) return (v * num) / (den + kEpsDenom);
+    const float v2 = v * v;
+    return v * ((num + 3.f * lam * v2) / (den + 2.f * lam * (v2 * v) + lam * v + kEpsDenom));
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
     // splitmix64 finaliser; identical to oracle/nmf_oracle.py:hash_uniform
     uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
                 const float* __restrict__ W, const float* __restrict__ G,
                 const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
-                int64_t d, int64_t n_loc, int kp) {
+                int64_t d, int64_t n_loc, int kp, float lam) {
     if (st->stop) return;
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
@@ -137,10 +137,10 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
         const int krow = kb0 + ty * TK + i;
         const float4 h = *reinterpret_cast<const float4*>(Hc + (int64_t)krow * ldh + col);
         float4 o;
-        o.x = (h.x * c[i][0]) / (dd[i][0] + kEpsDenom);
-        o.y = (col + 1 < n_loc) ? (h.y * c[i][1]) / (dd[i][1] + kEpsDenom) : 0.f;
-        o.z = (col + 2 < n_loc) ? (h.z * c[i][2]) / (dd[i][2] + kEpsDenom) : 0.f;
-        o.w = (col + 3 < n_loc) ? (h.w * c[i][3]) / (dd[i][3] + kEpsDenom) : 0.f;
+        o.x = mu_ratio(h.x, c[i][0], dd[i][0], lam);
+        o.y = (col + 1 < n_loc) ? mu_ratio(h.y, c[i][1], dd[i][1], lam) : 0.f;
+        o.z = (col + 2 < n_loc) ? mu_ratio(h.z, c[i][2], dd[i][2], lam) : 0.f;
+        o.w = (col + 3 < n_loc) ? mu_ratio(h.w, c[i][3], dd[i][3], lam) : 0.f;
         *reinterpret_cast<float4*>(Hn + (int64_t)krow * ldh + col) = o;
     }
 }
@@ -286,7 +286,7 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
 constexpr int UW_ROWS = 8;
 __global__ void __launch_bounds__(SIMT_THREADS)
 k_update_w(const DevState* __restrict__ st, const float* __restrict__ W, const float* __restrict__ A,
-           const float* __restrict__ B, float* __restrict__ Wn, int64_t d, int kp) {
+           const float* __restrict__ B, float* __restrict__ Wn, int64_t d, int kp, float lam) {
     if (st->stop) return;
     extern __shared__ float ws[];   // UW_ROWS x kp
     const int64_t row0 = (int64_t)blockIdx.x * UW_ROWS;
@@ -299,7 +299,7 @@ k_update_w(const DevState* __restrict__ st, const float* __restrict__ W, const f
         float s = 0.f;
         for (int l = 0; l < kp; ++l) s = fmaf(wr[l], B[(int64_t)l * kp + j], s);
         const int64_t o = (row0 + r) * kp + j;
-        Wn[o] = (wr[j] * A[o]) / (s + kEpsDenom);
+        Wn[o] = mu_ratio(wr[j], A[o], s, lam);
     }
 }
 

@@ -169,6 +169,10 @@ struct pymfb_ctx {
     int world = 1, rank = 0;
 
     int64_t launches = 0;
+    bool last_upload_pinned = false;
+
+    // BNMF penalty (pymf/bnmf.py:70-90): weights of the current iteration and their growth per H update; 0 = NMF
+    double lam_w = 0.0, lam_h = 0.0, inc_w = 1.0, inc_h = 1.0;
 
     // per-kernel timing (CUDA events on the launch stream)
     bool timing = false;
@@ -255,7 +259,7 @@ static int launch_update_w(pymfb_ctx* c) {
     const float* B = c->AB + c->d * c->kp;
     unsigned grid = (unsigned)((c->d + UW_ROWS - 1) / UW_ROWS);
     size_t smem = (size_t)UW_ROWS * c->kp * sizeof(float);
-    k_update_w<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, c->W[c->wcur], A, B, c->W[c->wcur ^ 1], c->d, c->kp);
+    k_update_w<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, c->W[c->wcur], A, B, c->W[c->wcur ^ 1], c->d, c->kp, (float)c->lam_w);
     c->launches += 1;
     CU(cudaGetLastError());
     c->wcur ^= 1;
@@ -268,23 +272,26 @@ static int launch_h_update(pymfb_ctx* c) {
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 0, &e0, &e1));
     if (c->path == PYMFB_PATH_TC) {
+        c->tc.lam_h = (float)c->lam_h;
         if (tc_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("tcgen05 H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
         if (c->kb == 16)
             k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h);
         else
             k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h);
         c->launches += 1;
         CU(cudaGetLastError());
     }
     CK(timing_end(c, 0, e0, e1));
     c->hcur ^= 1;
     c->ab_valid = false;
+    c->lam_w *= c->inc_w;      // pymf/bnmf.py:84-85: both weights grow at the end of update_h
+    c->lam_h *= c->inc_h;
     return 0;
 }
 
@@ -413,7 +420,7 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
             if (!c->g_valid) CK(launch_gram_w(c));
             // A, B of the new H feed the next W update and this iteration's error
             const bool need_ab = trace || (do_w && i + 1 < niter);
-            if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready) {
+            if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready && c->lam_h == 0.0) {
                 CK(launch_fused(c));
             } else {
                 CK(launch_h_update(c));
@@ -548,6 +555,20 @@ int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
     return fail("unknown option %d", option);
 }
 
+int pymfb_set_penalty(pymfb_ctx* c, double lamb_w, double lamb_h, double increase_w, double increase_h) {
+    if (!c) return fail("null context");
+    if (!(lamb_w >= 0.0) || !(lamb_h >= 0.0) || !(increase_w > 0.0) || !(increase_h > 0.0))
+        return fail("bad penalty lamb_w=%g lamb_h=%g increase_w=%g increase_h=%g", lamb_w, lamb_h, increase_w, increase_h);
+    c->lam_w = lamb_w; c->lam_h = lamb_h; c->inc_w = increase_w; c->inc_h = increase_h;
+    return 0;
+}
+int pymfb_get_penalty(pymfb_ctx* c, double* lamb_w, double* lamb_h) {
+    if (!c) return fail("null context");
+    if (lamb_w) *lamb_w = c->lam_w;
+    if (lamb_h) *lamb_h = c->lam_h;
+    return 0;
+}
+
 int pymfb_comm_unique_id(void* out128) {
     CK(nccl_load());
     NC(g_nccl.GetUniqueId(out128));
@@ -674,6 +695,73 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
     return 0;
 }
 
+// True when `p` is page-locked host memory the DMA engines can read directly (cudaHostAlloc,
+// cudaHostRegister, pymfb_host_alloc, torch pin_memory).
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Page-locked source: no host-side copy at all.  fp32 goes straight into X with one strided DMA;
+// fp64 is DMA'd in row chunks into two device staging buffers and cast to fp32 by k_cast_in while
+// the next chunk is in flight.
+static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
+    if (dtype == PYMFB_F32) {
+        CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float),
+                             (size_t)c->n_loc * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    const int NB = 2;
+    const int64_t row_bytes = c->n_loc * 8;
+    int64_t rows_per = std::min<int64_t>(c->d, std::max<int64_t>(1, (64LL << 20) / row_bytes));
+    double* dstage[NB] = {nullptr, nullptr};
+    cudaEvent_t cast_done[NB] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(c->stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        for (int b = 0; b < NB; ++b) { if (dstage[b]) cudaFree(dstage[b]); if (cast_done[b]) cudaEventDestroy(cast_done[b]); }
+        if (copied) cudaEventDestroy(copied);
+    };
+#define UP(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rc = fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+            cleanup();                                                                             \
+            return rc;                                                                             \
+        }                                                                                          \
+    } while (0)
+    UP(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    UP(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    for (int b = 0; b < NB; ++b) {
+        UP(cudaMalloc(&dstage[b], (size_t)rows_per * row_bytes));
+        UP(cudaEventCreateWithFlags(&cast_done[b], cudaEventDisableTiming));
+    }
+    // X_own was zeroed on c->stream by ensure_own_x; the casts run on c->stream, so order holds.
+    int64_t chunk = 0;
+    for (int64_t r0 = 0; r0 < c->d; r0 += rows_per, ++chunk) {
+        const int b = (int)(chunk % NB);
+        const int64_t nr = std::min(rows_per, c->d - r0);
+        if (chunk >= NB) UP(cudaStreamWaitEvent(copy_stream, cast_done[b], 0));   // staging buffer free again
+        UP(cudaMemcpy2DAsync(dstage[b], (size_t)row_bytes, (const char*)host + (size_t)r0 * ld * 8, (size_t)ld * 8,
+                             (size_t)row_bytes, (size_t)nr, cudaMemcpyHostToDevice, copy_stream));
+        UP(cudaEventRecord(copied, copy_stream));
+        UP(cudaStreamWaitEvent(c->stream, copied, 0));
+        k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
+            dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
+        c->launches += 1;
+        UP(cudaGetLastError());
+        UP(cudaEventRecord(cast_done[b], c->stream));
+    }
+#undef UP
+    cleanup();
+    return 0;
+}
+
 int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
     if (!c) return fail("null context");
     if (!x_host) return fail("x_host is null");
@@ -681,9 +769,25 @@ int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
     if (dtype != PYMFB_F32 && dtype != PYMFB_F64) return fail("bad dtype %d", dtype);
     CU(cudaSetDevice(c->device));
     CK(ensure_own_x(c));
-    CK(staged_upload(c, x_host, dtype, ld));
+    c->last_upload_pinned = host_is_pinned(x_host);
+    if (c->last_upload_pinned) CK(pinned_upload(c, x_host, dtype, ld));
+    else CK(staged_upload(c, x_host, dtype, ld));
     CU(cudaStreamSynchronize(c->stream));
     return data_changed(c);
+}
+
+int pymfb_last_upload_pinned(pymfb_ctx* c) { return c && c->last_upload_pinned ? 1 : 0; }
+
+int pymfb_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (pymfb_device_count() <= 0) return fail("no CUDA device available: page-locked memory needs the driver");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+int pymfb_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return 0;
 }
 
 int pymfb_gen_x(pymfb_ctx* c, uint64_t seed) {
@@ -790,6 +894,7 @@ int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n
         CU(cudaMalloc(&c->ferr_dev, sizeof(double) * c->ferr_cap));
     }
     const int w0 = c->wcur, h0 = c->hcur;
+    const double lw0 = c->lam_w, lh0 = c->lam_h;
     CK(enqueue_iterations(c, niter, flags));
     DevState hs;
     CU(cudaMemcpyAsync(&hs, c->st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
@@ -807,6 +912,10 @@ int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n
         c->g_valid = false;   // recomputed lazily for the surviving W
         c->ab_valid = false;
         c->tc.hs_valid[0] = c->tc.hs_valid[1] = false;
+        if (flags & PYMFB_COMPUTE_H) {   // the penalty weights grew once per EXECUTED update_h only
+            c->lam_w = lw0; c->lam_h = lh0;
+            for (int i = 0; i < done; ++i) { c->lam_w *= c->inc_w; c->lam_h *= c->inc_h; }
+        }
     }
     if (do_e && nf > 0) CU(cudaMemcpyAsync(ferr_host, c->ferr_dev, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

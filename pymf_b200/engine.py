@@ -19,6 +19,40 @@ def _dtype_code(a):
     raise TypeError("expected float32/float64, got %s" % a.dtype)
 
 
+class _PinnedBlock(object):
+    """Owner of one pymfb_host_alloc buffer; numpy arrays made by pinned_empty keep it alive."""
+
+    def __init__(self, nbytes):
+        self._lib = _lib.load()
+        self.ptr = C.c_void_p()
+        _lib.check(self._lib.pymfb_host_alloc(C.byref(self.ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and self.ptr.value:
+                self._lib.pymfb_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """Uninitialised numpy array in PAGE-LOCKED host memory (pymfb_host_alloc).
+
+    Build ``data`` in such an array (or in ``torch.empty(..., pin_memory=True).numpy()``) and
+    ``NMF(data, ...)`` uploads it with direct DMA - no host-side staging copy - instead of the
+    pageable path (the ``data[:,:]`` read of pymf/nmf.py:110,125,131 done once, at PCIe speed).
+    """
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
+    count = int(np.prod(shape)) if len(shape) else 1
+    block = _PinnedBlock(max(1, count * dtype.itemsize))
+    buf = (C.c_char * block.nbytes).from_address(block.ptr.value)
+    buf._pymfb_block = block                      # the ctypes buffer (numpy's .base) owns the allocation
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
 class Engine(object):
     def __init__(self, d, n_local, k, device=0, n_global=None, col0=0, path=None):
         self._lib = _lib.load()
@@ -56,6 +90,16 @@ class Engine(object):
         code = {"auto": _lib.ERR_AUTO, "trace": _lib.ERR_TRACE, "direct": _lib.ERR_DIRECT}.get(mode, mode)
         _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_ERR_MODE, int(code)))
 
+    def set_penalty(self, lamb_w, lamb_h, increase_w=1.0, increase_h=1.0):
+        """BNMF penalty weights of the next iteration and their growth per H update (pymf/bnmf.py:70-90)."""
+        _lib.check(self._lib.pymfb_set_penalty(self._ctx, float(lamb_w), float(lamb_h),
+                                               float(increase_w), float(increase_h)))
+
+    def get_penalty(self):
+        lw, lh = C.c_double(0.0), C.c_double(0.0)
+        _lib.check(self._lib.pymfb_get_penalty(self._ctx, C.byref(lw), C.byref(lh)))
+        return lw.value, lh.value
+
     @property
     def active_path(self):
         return {_lib.PATH_SIMT: "simt", _lib.PATH_TC: "tc"}.get(self._lib.pymfb_active_path(self._ctx), "?")
@@ -82,6 +126,11 @@ class Engine(object):
             x = np.ascontiguousarray(x)
         ld = x.strides[0] // x.itemsize
         _lib.check(self._lib.pymfb_upload_x(self._ctx, x.ctypes.data_as(C.c_void_p), _dtype_code(x), ld))
+
+    @property
+    def last_upload_pinned(self):
+        """True if the last upload_x read page-locked memory by direct DMA."""
+        return bool(self._lib.pymfb_last_upload_pinned(self._ctx))
 
     def bind_x_device(self, ptr, ld, keepalive=None):
         """Borrow a device pointer (fp32 row-major d x n_local, leading dimension ld)."""
@@ -113,13 +162,22 @@ class Engine(object):
         h = self._host_in(h, (self.k, self.n_local), "H")
         _lib.check(self._lib.pymfb_set_h(self._ctx, h.ctypes.data_as(C.c_void_p), _dtype_code(h)))
 
-    def get_w(self, dtype=np.float64):
-        out = np.empty((self.d, self.k), dtype=dtype)
+    @staticmethod
+    def _host_out(out, shape, dtype):
+        """Use `out` as the download target when it is a dense float32/float64 array of the right shape."""
+        if (isinstance(out, np.ndarray) and out.shape == shape and out.dtype in (np.float32, np.float64)
+                and out.flags.c_contiguous and out.flags.writeable):
+            return out
+        return np.empty(shape, dtype=dtype)
+
+    def get_w(self, dtype=np.float64, out=None):
+        """Current W as a host array; written straight into `out` when it is dense f32/f64 (no extra copy)."""
+        out = self._host_out(out, (self.d, self.k), dtype)
         _lib.check(self._lib.pymfb_get_w(self._ctx, out.ctypes.data_as(C.c_void_p), _dtype_code(out)))
         return out
 
-    def get_h(self, dtype=np.float64):
-        out = np.empty((self.k, self.n_local), dtype=dtype)
+    def get_h(self, dtype=np.float64, out=None):
+        out = self._host_out(out, (self.k, self.n_local), dtype)
         _lib.check(self._lib.pymfb_get_h(self._ctx, out.ctypes.data_as(C.c_void_p), _dtype_code(out)))
         return out
 

@@ -134,8 +134,10 @@ class NMF(object):
             raise AttributeError("'NMF' object has no attribute '%s'" % name)
         if f.dev_newer:
             eng = self._engine
-            fresh = eng.get_w(np.float64) if name == "W" else eng.get_h(np.float64)
-            f.host[...] = fresh                       # in place: `mdl.W is W` stays true
+            fresh = (eng.get_w(np.float64, out=f.host) if name == "W"
+                     else eng.get_h(np.float64, out=f.host))
+            if fresh is not f.host:
+                f.host[...] = fresh                   # in place: `mdl.W is W` stays true
             f.dev_newer = False
         f.host_dirty = True                           # handed out: the caller may mutate it
         return f.host

@@ -17,6 +17,8 @@ class FakeEngine(object):
         self.world, self.rank = 1, 0
         self.X = self.W = self.H = None
         self.uploads = {"x": 0, "w": 0, "h": 0}
+        self.lam = {"W": 0.0, "H": 0.0}
+        self.inc = (1.0, 1.0)
 
     # comm -------------------------------------------------------------------------------
     @staticmethod
@@ -35,6 +37,13 @@ class FakeEngine(object):
         dist.all_reduce(t)
         return t.numpy()
 
+    def set_penalty(self, lamb_w, lamb_h, increase_w=1.0, increase_h=1.0):
+        self.lam = {"W": float(lamb_w), "H": float(lamb_h)}
+        self.inc = (float(increase_w), float(increase_h))
+
+    def get_penalty(self):
+        return self.lam["W"], self.lam["H"]
+
     # data -------------------------------------------------------------------------------
     def upload_x(self, x):
         self.X = np.array(x, dtype=np.float64)
@@ -48,10 +57,10 @@ class FakeEngine(object):
         self.H = np.array(h, dtype=np.float64)
         self.uploads["h"] += 1
 
-    def get_w(self, dtype=np.float64):
+    def get_w(self, dtype=np.float64, out=None):
         return self.W.astype(dtype)
 
-    def get_h(self, dtype=np.float64):
+    def get_h(self, dtype=np.float64, out=None):
         return self.H.astype(dtype)
 
     # loop -------------------------------------------------------------------------------
@@ -67,7 +76,9 @@ class FakeEngine(object):
         nf = niter if compute_err else 0
         for i in range(niter):
             if compute_w:
-                if self.world == 1:
+                if self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
+                    O.bnmf_update_w(self.X, self.W, self.H, self.lam)
+                elif self.world == 1:
                     O.update_w(self.X, self.W, self.H)
                 else:
                     A = self._allreduce(self.X.dot(self.H.T))
@@ -76,7 +87,11 @@ class FakeEngine(object):
                     self.W *= A
                     self.W /= W2
             if compute_h:
-                O.update_h(self.X, self.W, self.H)
+                if self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
+                    assert self.inc == (O.LAMB_INCREASE_W, O.LAMB_INCREASE_H)
+                    O.bnmf_update_h(self.X, self.W, self.H, self.lam)
+                else:
+                    O.update_h(self.X, self.W, self.H)
             if compute_err:
                 ferr[i] = self._err()
             done = i + 1

@@ -52,3 +52,11 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_pinned_empty_fails_loudly_without_gpu():
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    import pymf_b200
+    with pytest.raises(pymf_b200.PymfbError, match="no CUDA device"):
+        pymf_b200.pinned_empty((4, 4))

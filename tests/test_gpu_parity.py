@@ -295,3 +295,46 @@ def test_fused_one_pass_kernel_matches_two_pass(shape, monkeypatch):
         assert rel(W, Wr) < TOL_WH and rel(H, Hr) < TOL_WH, (fused, rel(W, Wr), rel(H, Hr))
         assert np.max(np.abs(f - fr) / fr) < TOL_FERR, fused
     assert rel(res["1"][0], res["0"][0]) < 2e-5 and rel(res["1"][1], res["0"][1]) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pinned_ingest_equals_pageable_ingest(dtype):
+    """X from page-locked memory (direct DMA, pymfb_upload_x fast path) gives the same device
+    matrix as the pageable staging ring: identical trajectories, incl. a strided row view and a
+    row count that spans several fp64 staging chunks."""
+    d, n, k = 300, 70001, 8                       # 300 x 70001 f64 = 168 MB > 2 x 64 MB staging chunks
+    rng = np.random.RandomState(5)
+    base = pymf_b200.pinned_empty((d, n + 13), dtype)
+    base[...] = rng.random_sample((d, n + 13))
+    Xp = base[:, 5:5 + n]                         # strided view of pinned memory (ld = n + 13)
+    Xh = np.array(Xp)                             # pageable dense copy
+    W0 = rng.random_sample((d, k)); H0 = rng.random_sample((k, n))
+    out = []
+    for X, want_direct in ((Xp, True), (Xh, False)):
+        m = pymf_b200.NMF(X, num_bases=k)
+        m.W, m.H = W0.copy(), H0.copy()
+        m.factorize(niter=3)
+        assert m._engine.last_upload_pinned == want_direct
+        out.append((m.W.copy(), m.H.copy(), m.ferr.copy()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(Xh.astype(np.float64), Wr, Hr, niter=3)
+    assert rel(out[0][0], Wr) < TOL_WH and rel(out[0][1], Hr) < TOL_WH
+    assert np.max(np.abs(out[0][2] - fr) / fr) < TOL_FERR
+
+
+def test_factors_download_in_place_into_pinned_arrays():
+    d, n, k = 128, 1024, 16
+    rng = np.random.RandomState(6)
+    X = rng.random_sample((d, n))
+    W = pymf_b200.pinned_empty((d, k), np.float64); W[...] = rng.random_sample((d, k))
+    H = pymf_b200.pinned_empty((k, n), np.float32); H[...] = rng.random_sample((k, n))
+    Wr, Hr = W.copy(), H.astype(np.float64)
+    m = pymf_b200.NMF(X, num_bases=k)
+    m.W, m.H = W, H
+    m.factorize(niter=4)
+    assert m.W is W and m.H is H                  # identity kept, values written in place
+    O.factorize(X, Wr, Hr, niter=4)
+    assert rel(W, Wr) < TOL_WH and rel(H, Hr) < TOL_WH
