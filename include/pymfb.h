@@ -51,6 +51,14 @@ typedef struct pymfb_ctx pymfb_ctx;
 #define PYMFB_ERR_DIRECT 2     /* sqrt(sum((X - W H)^2)) as written in pymf/nmf.py:110: one more pass */
 #define PYMFB_OPT_ERR_MODE 2
 
+/* CUDA-graph replay of the iteration body (pymfb_set_option PYMFB_OPT_GRAPH).  Launch-bound
+ * problems (X up to 16 Mi elements, single rank, plain NMF) replay two iterations - one ping-pong
+ * period of the W / H buffers - as one cudaGraphLaunch; results are those of the plain launches. */
+#define PYMFB_GRAPH_AUTO 0     /* small problems only */
+#define PYMFB_GRAPH_OFF  1
+#define PYMFB_GRAPH_ON   2     /* whenever the loop is replayable (any size) */
+#define PYMFB_OPT_GRAPH 3
+
 /* Library / ABI version (major*1000 + minor). */
 int pymfb_version(void);
 
@@ -79,7 +87,7 @@ int pymfb_set_option(pymfb_ctx* ctx, int option, int64_t value);
  *           W <- W * (X H^T + 3 lamb_w W^2) / (W B + 2 lamb_w W^3 + lamb_w W + 1e-9)   (:87-90)
  * and after every H update lamb_w *= increase_w, lamb_h *= increase_h (:84-85; BNMF.factorize
  * starts both at 1/niter, :117-118, with _LAMB_INCREASE_W/H = 1.1, :75-76).  lamb = 0 (the
- * default) is plain NMF, bit-identical to not calling this.  get_penalty returns the current
+ * default) is plain NMF (the same arithmetic as not calling this).  get_penalty returns the current
  * weights (the reference's _lamb_W / _lamb_H after factorize).
  */
 int pymfb_set_penalty(pymfb_ctx* ctx, double lamb_w, double lamb_h, double increase_w, double increase_h);
@@ -173,6 +181,10 @@ int pymfb_kernel_timing_read(pymfb_ctx* ctx, int which, double* avg_ms, int64_t*
 
 /* Kernel launches issued by this context so far (all kernels of this library). */
 int64_t pymfb_launch_count(pymfb_ctx* ctx);
+
+/* Graph launches issued so far (each replays two iterations; their kernels are included in
+ * pymfb_launch_count). */
+int64_t pymfb_graph_replays(pymfb_ctx* ctx);
 
 /* Which path the context resolved to for its shape: PYMFB_PATH_SIMT or PYMFB_PATH_TC. */
 int pymfb_active_path(pymfb_ctx* ctx);

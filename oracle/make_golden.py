@@ -92,6 +92,25 @@ def main_bnmf():
     refb = load_reference_bnmf()
     if refb is None:
         sys.exit("no reference checkout found (set PYMF_REF)")
+    # the reference's own BNMF test vector (tests/test_pymf.py:80,84-95): np.round(A - 2.0), k = 4, niter = 20,
+    # then the flag combinations and a warm restart
+    A = np.round(cases.ref_test_matrix() - 2.0)
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    m = refb.BNMF(A, num_bases=4)
+    m.factorize(niter=20)
+    out = {"W_20": m.W.copy(), "H_20": m.H.copy(), "ferr_20": m.ferr.copy()}
+    assert out["ferr_20"][-1] / 53 < 0.1                     # the reference's bound, :86-88
+    m.factorize(compute_h=False, niter=20)                   # :92
+    out.update(W_a=m.W.copy(), H_a=m.H.copy(), ferr_a=m.ferr.copy())
+    m.factorize(compute_w=False, niter=20)                   # :93
+    out.update(W_b=m.W.copy(), H_b=m.H.copy(), ferr_b=m.ferr.copy())
+    m.factorize(compute_err=False, niter=20)                 # :94
+    out.update(W_c=m.W.copy(), H_c=m.H.copy(), ferr_c=m.ferr.copy())
+    m.factorize(niter=20)                                    # :95
+    out.update(W_d=m.W.copy(), H_d=m.H.copy(), ferr_d=m.ferr.copy(), lam_d=np.array([m._lamb_W, m._lamb_H]))
+    np.savez(os.path.join(OUT, "bnmf_ref_test_3x50.npz"), **out)
+    print("bnmf ref test: ferr[-1]/53 =", out["ferr_20"][-1] / 53, "lens", [len(out[k_]) for k_ in ("ferr_20", "ferr_a", "ferr_b", "ferr_c", "ferr_d")])
+
     for name, c in cases.BNMF_CASES.items():
         X, W0, H0 = cases.build(name)
         X = X.astype(np.float64)

@@ -17,6 +17,8 @@ COMPUTE_W, COMPUTE_H, COMPUTE_ERR, EARLY_STOP = 1, 2, 4, 8
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 OPT_PATH = 1
 OPT_ERR_MODE = 2
+OPT_GRAPH = 3
+GRAPH_AUTO, GRAPH_OFF, GRAPH_ON = 0, 1, 2
 ERR_AUTO, ERR_TRACE, ERR_DIRECT = 0, 1, 2
 
 _c_ctx = C.c_void_p
@@ -59,6 +61,7 @@ SIGNATURES = {
     "pymfb_kernel_timing": (C.c_int, [_c_ctx, C.c_int]),
     "pymfb_kernel_timing_read": (C.c_int, [_c_ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "pymfb_launch_count": (_i64, [_c_ctx]),
+    "pymfb_graph_replays": (_i64, [_c_ctx]),
     "pymfb_active_path": (C.c_int, [_c_ctx]),
     "pymfb_flush_l2": (C.c_int, [_c_ctx]),
 }

@@ -22,13 +22,14 @@ struct DevState {
     double resid_local;  // direct-residual mode: this rank's sum (X - W H)^2
     double resid;        // ... summed over ranks
     unsigned ticket3;    // last-block-done counter of the direct residual
-    unsigned pad_;
+    int it;              // iteration index inside the current run: k_err stores ferr[it] and advances it, so the
+                         // per-iteration launch sequence carries no host-side index (replayable as a CUDA graph)
 };
 
 // The multiplicative ratio shared by every update kernel.  num = W^T X (or X H^T), den = G H (or W B).
 //   lam == 0 : NMF   v * num / (den + 1e-9)                                        pymf/nmf.py:124-126, 130-132
 //   lam != 0 : BNMF  v * ((num + 3 lam v^2) / (den + 2 lam v^3 + lam v + 1e-9))    pymf/bnmf.py:79-82, 87-90
-// (lam is uniform over the launch, so the branch does not diverge; lam == 0 keeps NMF bit-identical.)
+// (lam is uniform over the launch, so the branch does not diverge; lam == 0 is exactly the NMF expression.)
 __device__ __forceinline__ float mu_ratio(float v, float num, float den, float lam) {
     if (lam == 0.f) return (v * num) / (den + kEpsDenom);
     const float v2 = v * v;

@@ -313,7 +313,7 @@ constexpr int ERR_BLOCKS = 128;
 __global__ void __launch_bounds__(256)
 k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __restrict__ A,
       int64_t n_wa, const float* __restrict__ G, const float* __restrict__ B, int64_t n_gb,
-      double* __restrict__ scratch /* 2*ERR_BLOCKS */, double* __restrict__ ferr, int iter,
+      double* __restrict__ scratch /* 2*ERR_BLOCKS */, double* __restrict__ ferr,
       double n_samples, int early_stop, int direct) {
     if (st->stop) return;
     __shared__ double s_wa[256], s_gb[256];
@@ -351,6 +351,8 @@ k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __res
         st->last_ferr = e;
         st->ticket = 0;
         if (ferr) {
+            const int iter = st->it;       // device-side iteration counter (reset by the host at the start of a run)
+            st->it = iter + 1;
             ferr[iter] = e;
             if (early_stop && iter > 1) {
                 double derr = fabs(e - ferr[iter - 1]) / n_samples;

@@ -119,6 +119,14 @@ static int nccl_load() {
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
+// Host-side scheduling state that decides which kernels an iteration launches and on which buffers.
+struct LoopState {
+    int wcur, hcur; bool ab, g, xx, hs0, hs1;
+    bool operator==(const LoopState& o) const {
+        return wcur == o.wcur && hcur == o.hcur && ab == o.ab && g == o.g && xx == o.xx && hs0 == o.hs0 && hs1 == o.hs1;
+    }
+};
+
 struct pymfb_ctx {
     int device = 0;
     int64_t d = 0, n_loc = 0, n_glob = 0, col0 = 0;
@@ -170,6 +178,15 @@ struct pymfb_ctx {
 
     int64_t launches = 0;
     bool last_upload_pinned = false;
+    void* stage = nullptr;         // factor transfer staging (factor_stage)
+    size_t stage_bytes = 0;
+
+    // CUDA graph of two steady-state iterations (launch-bound problems), see graph_build
+    int graph_opt = PYMFB_GRAPH_AUTO;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned graph_key = 0;
+    LoopState graph_state = {0, 0, false, false, false, false, false};
+    int64_t graph_launches = 0, graph_replays = 0;
 
     // BNMF penalty (pymf/bnmf.py:70-90): weights of the current iteration and their growth per H update; 0 = NMF
     double lam_w = 0.0, lam_h = 0.0, inc_w = 1.0, inc_h = 1.0;
@@ -370,7 +387,7 @@ static int launch_xx(pymfb_ctx* c) {
     return 0;
 }
 
-static int launch_err(pymfb_ctx* c, int iter, bool store, bool early_stop) {
+static int launch_err(pymfb_ctx* c, bool store, bool early_stop) {
     const float* A = c->AB;
     const float* B = c->AB + c->d * c->kp;
     if (c->err_direct) {
@@ -386,10 +403,10 @@ static int launch_err(pymfb_ctx* c, int iter, bool store, bool early_stop) {
         if (c->world > 1)
             NC(g_nccl.AllReduce(&c->st->resid_local, &c->st->resid, 1, kNcclFloat64, kNcclSum, c->comm, c->stream));
         k_err<<<1, 256, 0, c->stream>>>(c->st, nullptr, nullptr, 0, nullptr, nullptr, 0, c->red_scratch,
-                                        store ? c->ferr_dev : nullptr, iter, (double)c->n_glob, early_stop ? 1 : 0, 1);
+                                        store ? c->ferr_dev : nullptr, (double)c->n_glob, early_stop ? 1 : 0, 1);
     } else {
         k_err<<<ERR_BLOCKS, 256, 0, c->stream>>>(c->st, c->W[c->wcur], A, c->d * c->kp, c->G, B, (int64_t)c->kp * c->kp,
-                                                 c->red_scratch, store ? c->ferr_dev : nullptr, iter,
+                                                 c->red_scratch, store ? c->ferr_dev : nullptr,
                                                  (double)c->n_glob, early_stop ? 1 : 0, 0);
     }
     c->launches += 1;
@@ -404,35 +421,105 @@ static int check_ready(pymfb_ctx* c) {
     return 0;
 }
 
+// One iteration of the factorize() loop (pymf/nmf.py:182-190): W update, H update, error.
+// more_after: another iteration follows (its W update needs A, B of the new H).
+static int enqueue_one(pymfb_ctx* c, bool do_w, bool do_h, bool do_e, bool trace, bool early, bool more_after) {
+    if (do_w) {
+        if (!c->ab_valid) CK(launch_xht(c));      // bootstrap: A, B of the current H
+        CK(launch_update_w(c));
+    }
+    if (do_h) {
+        if (!c->g_valid) CK(launch_gram_w(c));
+        // A, B of the new H feed the next W update and this iteration's error
+        const bool need_ab = trace || (do_w && more_after);
+        if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready && c->lam_h == 0.0) {
+            CK(launch_fused(c));
+        } else {
+            CK(launch_h_update(c));
+            if (need_ab) CK(launch_xht(c));
+        }
+    }
+    if (do_e) {
+        if (trace && !c->g_valid) CK(launch_gram_w(c));
+        if (trace && !c->ab_valid) CK(launch_xht(c));
+        CK(launch_err(c, true, early));
+    }
+    return 0;
+}
+
+static LoopState loop_state(const pymfb_ctx* c) {
+    return LoopState{c->wcur, c->hcur, c->ab_valid, c->g_valid, c->xx_valid, c->tc.hs_valid[0], c->tc.hs_valid[1]};
+}
+
+static void graph_drop(pymfb_ctx* c) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+}
+
+// Launch-bound problems (an iteration is ~10 kernels of a few microseconds each: cfg1 1000 x 500 ran 108 us per
+// iteration, almost all of it launch gaps) replay TWO iterations - one full ping-pong period of the W / H buffers -
+// as one CUDA graph.  Eligible: single rank, plain NMF (the BNMF weight changes every iteration), no per-kernel
+// timing, small X.  The graph is captured from the steady state (after two plain iterations) and cached.
+static bool graph_eligible(const pymfb_ctx* c, int niter) {
+    if (c->graph_opt == PYMFB_GRAPH_OFF) return false;
+    if (c->world > 1 || c->timing || c->lam_w != 0.0 || c->lam_h != 0.0 || niter < 5) return false;
+    if (c->path == PYMFB_PATH_TC && c->fused.ready) return false;
+    if (c->graph_opt == PYMFB_GRAPH_ON) return true;
+    return (double)c->d * (double)c->n_loc <= 16777216.0;
+}
+
+static int graph_build(pymfb_ctx* c, unsigned key, bool do_w, bool do_h, bool do_e, bool trace, bool early) {
+    graph_drop(c);
+    const LoopState s0 = loop_state(c);
+    const int64_t l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_one(c, do_w, do_h, do_e, trace, early, true);
+    if (!rc) rc = enqueue_one(c, do_w, do_h, do_e, trace, early, true);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    const int64_t per = c->launches - l0;
+    c->launches = l0;                              // nothing ran yet
+    const bool periodic = loop_state(c) == s0;
+    // capture only recorded the launches: put the scheduling state back to where the stream really is
+    c->wcur = s0.wcur; c->hcur = s0.hcur; c->ab_valid = s0.ab; c->g_valid = s0.g; c->xx_valid = s0.xx;
+    c->tc.hs_valid[0] = s0.hs0; c->tc.hs_valid[1] = s0.hs1;
+    if (rc || e != cudaSuccess || !g || !periodic) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->graph_key = 0xFFFFFFFFu;                // do not retry for this flag set / state
+        c->graph_state = s0;
+        return 0;                                  // not an error: the caller falls back to plain launches
+    }
+    e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { c->graph_exec = nullptr; cudaGetLastError(); return 0; }
+    c->graph_key = key; c->graph_state = s0; c->graph_launches = per;
+    return 0;
+}
+
 static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
     CK(check_ready(c));
     CU(cudaSetDevice(c->device));
     const bool do_w = flags & PYMFB_COMPUTE_W, do_h = flags & PYMFB_COMPUTE_H, do_e = flags & PYMFB_COMPUTE_ERR;
     const bool early = (flags & PYMFB_EARLY_STOP) && do_e;
     const bool trace = do_e && !c->err_direct;   // the trace identity needs ||X||^2, A, B, G
+    if (do_e) CU(cudaMemsetAsync(&c->st->it, 0, sizeof(int), c->stream));
     if (trace && !c->xx_valid) CK(launch_xx(c));
-    for (int i = 0; i < niter; ++i) {
-        if (do_w) {
-            if (!c->ab_valid) CK(launch_xht(c));      // bootstrap: A, B of the current H
-            CK(launch_update_w(c));
-        }
-        if (do_h) {
-            if (!c->g_valid) CK(launch_gram_w(c));
-            // A, B of the new H feed the next W update and this iteration's error
-            const bool need_ab = trace || (do_w && i + 1 < niter);
-            if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready && c->lam_h == 0.0) {
-                CK(launch_fused(c));
-            } else {
-                CK(launch_h_update(c));
-                if (need_ab) CK(launch_xht(c));
+    int i = 0;
+    if (graph_eligible(c, niter)) {
+        for (; i < 2; ++i) CK(enqueue_one(c, do_w, do_h, do_e, trace, early, true));   // reach the steady state (both ping-pong halves)
+        const unsigned key = (do_w ? 1u : 0u) | (do_h ? 2u : 0u) | (do_e ? 4u : 0u) | (early ? 8u : 0u) | (trace ? 16u : 0u);
+        if (!(c->graph_exec && c->graph_key == key && c->graph_state == loop_state(c)) &&
+            !(c->graph_key == 0xFFFFFFFFu && c->graph_state == loop_state(c)))
+            CK(graph_build(c, key, do_w, do_h, do_e, trace, early));
+        if (c->graph_exec && c->graph_key == key && c->graph_state == loop_state(c)) {
+            for (; i + 2 < niter; i += 2) {        // the last iteration stays outside (more_after = false)
+                CU(cudaGraphLaunch(c->graph_exec, c->stream));
+                c->launches += c->graph_launches;
+                c->graph_replays += 1;
             }
         }
-        if (do_e) {
-            if (trace && !c->g_valid) CK(launch_gram_w(c));
-            if (trace && !c->ab_valid) CK(launch_xht(c));
-            CK(launch_err(c, i, true, early));
-        }
     }
+    for (; i < niter; ++i) CK(enqueue_one(c, do_w, do_h, do_e, trace, early, i + 1 < niter));
     return 0;
 }
 
@@ -516,13 +603,14 @@ int pymfb_destroy(pymfb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    graph_drop(c);
     tc_release(c->tc);
     fused_release(c->fused);
     for (int w = 0; w < 2; ++w)
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->AB != c->P) cudaFree(c->AB);
     cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
-    cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
+    cudaFree(c->stage); cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
     for (int i = 0; i < 2; ++i) { cudaFree(c->W[i]); cudaFree(c->H[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
@@ -531,6 +619,12 @@ int pymfb_destroy(pymfb_ctx* c) {
 
 int pymfb_set_option(pymfb_ctx* c, int option, int64_t value) {
     if (!c) return fail("null context");
+    graph_drop(c); c->graph_key = 0;          // every option changes which kernels an iteration launches
+    if (option == PYMFB_OPT_GRAPH) {
+        if (value < 0 || value > 2) return fail("bad graph option %lld", (long long)value);
+        c->graph_opt = (int)value;
+        return 0;
+    }
     if (option == PYMFB_OPT_PATH) {
         if (value < 0 || value > 2) return fail("bad path option %lld", (long long)value);
         c->path_opt = (int)value;
@@ -592,6 +686,7 @@ int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
 }
 
 static int data_changed(pymfb_ctx* c) {
+    graph_drop(c); c->graph_key = 0;
     c->ab_valid = false; c->xx_valid = false;
     CK(resolve_path(c));
     if (c->path == PYMFB_PATH_TC) CK(plan_tc(c));
@@ -708,8 +803,11 @@ static bool host_is_pinned(const void* p) {
 // the next chunk is in flight.
 static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
     if (dtype == PYMFB_F32) {
-        CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float),
-                             (size_t)c->n_loc * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+        if (ld == c->n_loc && c->ldx == c->n_loc)
+            CU(cudaMemcpyAsync(c->X_own, host, (size_t)c->d * c->n_loc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        else
+            CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float),
+                                 (size_t)c->n_loc * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
         return 0;
     }
     const int NB = 2;
@@ -801,6 +899,18 @@ int pymfb_gen_x(pymfb_ctx* c, uint64_t seed) {
     return data_changed(c);
 }
 
+// Device staging buffer of the factor transfers (grow-only, owned by the context: a cudaMalloc / cudaFree pair
+// per set/get call showed up as 10 - 1000 ms stalls next to the frees of a previous 4 GiB engine).
+static int factor_stage(pymfb_ctx* c, size_t bytes, void** out) {
+    if (bytes > c->stage_bytes) {
+        if (c->stage) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->stage)); c->stage = nullptr; c->stage_bytes = 0; }
+        CU(cudaMalloc(&c->stage, bytes));
+        c->stage_bytes = bytes;
+    }
+    *out = c->stage;
+    return 0;
+}
+
 // host (rows x cols, dense, dtype) -> device fp32 (rows x ldd), padding zeroed
 static int set_factor(pymfb_ctx* c, float* dst, int64_t ldd, int64_t rows_alloc, int64_t rows, int64_t cols,
                       const void* host, int dtype) {
@@ -809,7 +919,7 @@ static int set_factor(pymfb_ctx* c, float* dst, int64_t ldd, int64_t rows_alloc,
     CU(cudaSetDevice(c->device));
     const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
     void* stage = nullptr;
-    CU(cudaMalloc(&stage, (size_t)rows * cols * esz));
+    CK(factor_stage(c, (size_t)rows * cols * esz, &stage));
     CU(cudaMemcpyAsync(stage, host, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(dst, 0, (size_t)rows_alloc * ldd * sizeof(float), c->stream));
     const int g = grid_for(rows * cols, 256, 16 * c->sm_count);
@@ -818,7 +928,6 @@ static int set_factor(pymfb_ctx* c, float* dst, int64_t ldd, int64_t rows_alloc,
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(stage));
     return 0;
 }
 static int get_factor(pymfb_ctx* c, const float* src, int64_t lds, int64_t rows, int64_t cols, void* host, int dtype) {
@@ -827,7 +936,7 @@ static int get_factor(pymfb_ctx* c, const float* src, int64_t lds, int64_t rows,
     CU(cudaSetDevice(c->device));
     const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
     void* stage = nullptr;
-    CU(cudaMalloc(&stage, (size_t)rows * cols * esz));
+    CK(factor_stage(c, (size_t)rows * cols * esz, &stage));
     const int g = grid_for(rows * cols, 256, 16 * c->sm_count);
     if (dtype == PYMFB_F32) k_cast_out<float><<<g, 256, 0, c->stream>>>(src, lds, (float*)stage, cols, rows, cols);
     else k_cast_out<double><<<g, 256, 0, c->stream>>>(src, lds, (double*)stage, cols, rows, cols);
@@ -835,7 +944,6 @@ static int get_factor(pymfb_ctx* c, const float* src, int64_t lds, int64_t rows,
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host, stage, (size_t)rows * cols * esz, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(stage));
     return 0;
 }
 
@@ -890,6 +998,7 @@ int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n
     CU(cudaSetDevice(c->device));
     if (do_e && niter > c->ferr_cap) {
         if (c->ferr_dev) CU(cudaFree(c->ferr_dev));
+        graph_drop(c); c->graph_key = 0;       // the graph holds the old ferr pointer
         c->ferr_cap = std::max(niter, 1024);
         CU(cudaMalloc(&c->ferr_dev, sizeof(double) * c->ferr_cap));
     }
@@ -933,7 +1042,7 @@ int pymfb_frobenius(pymfb_ctx* c, double* out) {
         if (!c->g_valid) CK(launch_gram_w(c));
         if (!c->ab_valid) CK(launch_xht(c));
     }
-    CK(launch_err(c, 0, false, false));
+    CK(launch_err(c, false, false));
     DevState hs;
     CU(cudaMemcpyAsync(&hs, c->st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -946,6 +1055,7 @@ int pymfb_enqueue(pymfb_ctx* c, int niter, unsigned flags) {
     if ((flags & PYMFB_COMPUTE_ERR) && niter > c->ferr_cap) {
         CU(cudaSetDevice(c->device));
         if (c->ferr_dev) CU(cudaFree(c->ferr_dev));
+        graph_drop(c); c->graph_key = 0;       // the graph holds the old ferr pointer
         c->ferr_cap = std::max(niter, 1024);
         CU(cudaMalloc(&c->ferr_dev, sizeof(double) * c->ferr_cap));
     }
@@ -1006,6 +1116,7 @@ int pymfb_kernel_timing_read(pymfb_ctx* c, int which, double* avg_ms, int64_t* l
 }
 
 int64_t pymfb_launch_count(pymfb_ctx* c) { return c ? c->launches : 0; }
+int64_t pymfb_graph_replays(pymfb_ctx* c) { return c ? c->graph_replays : 0; }
 int pymfb_active_path(pymfb_ctx* c) { return c ? c->path : 0; }
 
 int pymfb_flush_l2(pymfb_ctx* c) {

@@ -90,6 +90,15 @@ class Engine(object):
         code = {"auto": _lib.ERR_AUTO, "trace": _lib.ERR_TRACE, "direct": _lib.ERR_DIRECT}.get(mode, mode)
         _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_ERR_MODE, int(code)))
 
+    def set_graph_mode(self, mode):
+        """'auto' (small problems) | 'off' | 'on': CUDA-graph replay of the iteration body."""
+        code = {"auto": _lib.GRAPH_AUTO, "off": _lib.GRAPH_OFF, "on": _lib.GRAPH_ON}.get(mode, mode)
+        _lib.check(self._lib.pymfb_set_option(self._ctx, _lib.OPT_GRAPH, int(code)))
+
+    @property
+    def graph_replays(self):
+        return int(self._lib.pymfb_graph_replays(self._ctx))
+
     def set_penalty(self, lamb_w, lamb_h, increase_w=1.0, increase_h=1.0):
         """BNMF penalty weights of the next iteration and their growth per H update (pymf/bnmf.py:70-90)."""
         _lib.check(self._lib.pymfb_set_penalty(self._ctx, float(lamb_w), float(lamb_h),

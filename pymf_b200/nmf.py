@@ -15,6 +15,7 @@ Differences that are deliberate and documented in DESIGN.md:
     ``-123456`` sentinel for it, :109-112).
 """
 import logging
+import sys
 
 import numpy as np
 
@@ -26,9 +27,11 @@ _SENTINEL = -123456      # pymf/nmf.py:112
 
 
 def _is_sparse(a):
+    # A scipy sparse matrix can only exist if scipy.sparse is already imported; never import it here
+    # (the first import costs ~0.15 s, which used to land inside the first factorize()).
+    sp = sys.modules.get("scipy.sparse")
     try:
-        import scipy.sparse
-        return scipy.sparse.issparse(a)
+        return sp is not None and bool(sp.issparse(a))
     except Exception:
         return False
 
@@ -173,8 +176,8 @@ class NMF(object):
 
     def _upload_data(self):
         x = self._data
-        try:
-            import torch
+        torch = sys.modules.get("torch")             # a torch.Tensor implies torch is imported; never import it here
+        if torch is not None:
             if isinstance(x, torch.Tensor):
                 if x.is_cuda:
                     if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
@@ -185,8 +188,6 @@ class NMF(object):
                     self._engine.bind_x_device(x.data_ptr(), x.stride(0), keepalive=x)
                     return
                 x = x.numpy()
-        except ImportError:
-            pass
         if not isinstance(x, np.ndarray):
             x = np.asarray(x[:, :])                  # h5py-style sources, pymf/nmf.py:110,125,131
         self._engine.upload_x(x)
