@@ -296,26 +296,39 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
             Xh = rng.random((d, n_loc), dtype=np.float32)
             W0 = rng.random((d, k))
             H0 = rng.random((k, n_loc))
-        m = pymf_b200.NMF(Xh, num_bases=k, device=local_rank, path=args.path,
-                          process_group=(True if world > 1 else None))
-        barrier()
-        t0 = time.perf_counter()
-        m.W, m.H = W0, H0
-        m._sync_to_device()            # X / W / H host -> device (part of factorize; split out for the breakdown)
-        t1 = time.perf_counter()
-        m.factorize(niter=steps)
-        t2 = time.perf_counter()
-        _ = (m.W, m.H, m.ferr)
-        torch.cuda.synchronize()
-        t3 = time.perf_counter()
-        t_e2e = max_over_ranks(t3 - t0)
+        # Two passes of the identical user-level sequence; the second is the one reported.  The first pays this
+        # process's one-off costs for a matrix of this size (first 4 GiB device allocation and DMA mapping: measured
+        # 0.18-0.29 s vs 0.116 s, tests/_e2e_probe2.py) and is reported beside it as `first_call_seconds`.
+        rec = []
+        for _pass in range(2):
+            m = pymf_b200.NMF(Xh, num_bases=k, device=local_rank, path=args.path,
+                              process_group=(True if world > 1 else None))
+            barrier()
+            t0 = time.perf_counter()
+            m.W, m.H = W0, H0
+            m._sync_to_device()        # X / W / H host -> device (part of factorize; split out for the breakdown)
+            t1 = time.perf_counter()
+            m.factorize(niter=steps)
+            t2 = time.perf_counter()
+            _ = (m.W, m.H, m.ferr)
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            rec.append((max_over_ranks(t3 - t0), t1 - t0, t2 - t1, t3 - t2, bool(m._engine.last_upload_pinned)))
+            del m
+            if _pass == 0:             # fresh starting factors for the reported pass (W0 / H0 were updated in place)
+                rng = np.random.default_rng(4321 + rank)
+                W0[...] = rng.random(W0.shape)
+                H0[...] = rng.random(H0.shape)
+        t_e2e, t_up, t_it, t_dn, direct = rec[1]
         h2d = (Xh.nbytes + W0.nbytes + H0.nbytes) / float(steps)
         d2h = (W0.nbytes + H0.nbytes + 8 * steps) / float(steps)
         e2e = {"value": units_per_step * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "seconds_total": t_e2e,
-               "seconds_upload": t1 - t0, "seconds_iterations": t2 - t1, "seconds_download": t3 - t2,
-               "host_source": args.e2e_source, "x_upload_direct_dma": bool(m._engine.last_upload_pinned),
-               "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download" % steps}
+               "seconds_upload": t_up, "seconds_iterations": t_it, "seconds_download": t_dn,
+               "first_call_seconds": rec[0][0],
+               "host_source": args.e2e_source, "x_upload_direct_dma": direct,
+               "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download; second of two "
+                       "identical calls in this process" % steps}
         del m
 
     # ---- CPU baseline (rank 0, N = 1 only)

@@ -94,6 +94,20 @@ int pymfb_set_penalty(pymfb_ctx* ctx, double lamb_w, double lamb_h, double incre
 int pymfb_get_penalty(pymfb_ctx* ctx, double* lamb_w, double* lamb_h);
 
 /*
+ * Semi-NMF - another override of the same two hooks (pymf/snmf.py:22-90): X and W may be signed,
+ * H stays non-negative.  With PYMFB_VARIANT_SNMF the loop's steps become
+ *   W <- (X H^T) (H H^T)^-1                                                         (:67-70)
+ *   H <- H * sqrt(((W^T X)+ + G- H) / ((W^T X)- + G+ H + 1e-9)),  G = W^T W,
+ *        m+ = (|m| + m)/2, m- = (|m| - m)/2                                         (:72-90)
+ * on the same passes: the X H^T / H H^T reductions feed a fp64 k x k inverse (k <= 128), the
+ * H-update pass keeps its W^T X contraction and switches its epilogue.  Error, early stop, flags
+ * and sharding are those of NMF.
+ */
+#define PYMFB_VARIANT_NMF  0
+#define PYMFB_VARIANT_SNMF 1
+int pymfb_set_variant(pymfb_ctx* ctx, int variant);
+
+/*
  * Multi-GPU (one process per GPU).  Rank 0 calls pymfb_comm_unique_id (128 bytes, an
  * ncclUniqueId), the host layer broadcasts it, every rank calls pymfb_comm_init.
  * After that pymfb_prepare / pymfb_run sum the packed [X H^T | H H^T] partials (and

@@ -48,8 +48,18 @@ BNMF_CASES = {
 }
 
 
+# SNMF parity cases (pymf/snmf.py).  kind "npc" / "hashc": the data is CENTERED (X - 0.5, signed entries), which
+# is what semi-NMF is for; W0/H0 ~ U[0,1).
+SNMF_CASES = {
+    "snmf_signed": dict(kind="npc", seed=31, d=40, n=150, k=4, niter=15, keep=[1, 5, 15]),
+    "snmf_ragged": dict(kind="np", seed=33, d=37, n=201, k=5, niter=12, keep=[1, 12]),
+    "snmf_tc": dict(kind="hashc", seed=61, d=512, n=640, k=32, niter=8, keep=[1, 8], store32=True),
+    "snmf_k40": dict(kind="hash", seed=63, d=300, n=1000, k=40, niter=6, keep=[1, 6], store32=True),
+}
+
+
 def build(name):
-    c = CASES[name] if name in CASES else BNMF_CASES[name]
+    c = CASES[name] if name in CASES else (BNMF_CASES[name] if name in BNMF_CASES else SNMF_CASES[name])
     d, n, k = c["d"], c["n"], c["k"]
     if c["kind"] == "bin":
         np.random.seed(c["seed"])
@@ -58,13 +68,15 @@ def build(name):
         X = (Ws.dot(Hs) > 0).astype(np.float64)
         W0 = np.random.random((d, k))
         H0 = np.random.random((k, n))
-    elif c["kind"] == "np":
+    elif c["kind"] in ("np", "npc"):
         np.random.seed(c["seed"])
-        X = np.random.random((d, n))
+        X = np.random.random((d, n)) - (0.5 if c["kind"] == "npc" else 0.0)
         W0 = np.random.random((d, k))
         H0 = np.random.random((k, n))
     else:
         X = gen_matrix(c["seed"], d, n)
+        if c["kind"] == "hashc":
+            X = X - np.float32(0.5)
         W0 = gen_matrix(c["seed"] + 1, d, k).astype(np.float64)
         H0 = gen_matrix(c["seed"] + 2, k, n).astype(np.float64)
     return X, W0, H0

@@ -14,15 +14,15 @@ import sys
 import numpy as np
 
 from . import cases
-from .ref_loader import load_reference_bnmf, load_reference_nmf
+from .ref_loader import load_reference_bnmf, load_reference_nmf, load_reference_snmf
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def run_steps(ref, X, W0, H0, k, niter, keep):
+def run_steps(ref, X, W0, H0, k, niter, keep, cls="NMF"):
     """Single-step the reference (factorize(niter=1) never triggers the early stop,
     SURVEY 3.4) and record ferr per iteration and W/H at the iterations in keep."""
-    m = ref.NMF(X, num_bases=k)
+    m = getattr(ref, cls)(X, num_bases=k)
     m.W = W0.copy()
     m.H = H0.copy()
     ferr = np.zeros(niter)
@@ -140,8 +140,44 @@ def main_bnmf():
         print(name, "ferr", ferr[0], "->", ferr[-1], "len(ferr_whole)", len(f.ferr), "lam", f._lamb_H)
 
 
+def main_snmf():
+    """SNMF fixtures from the unmodified pymf/snmf.py: the reference's own test vector
+    (tests/test_pymf.py:77,84-95) and stepped trajectories of the seeded cases."""
+    refs = load_reference_snmf()
+    if refs is None:
+        sys.exit("no reference checkout found (set PYMF_REF)")
+    A = cases.ref_test_matrix()
+    np.random.seed(cases.REF_TEST_INIT_SEED)
+    m = refs.SNMF(A, num_bases=4)
+    m.factorize(niter=20)
+    out = {"W_20": m.W.copy(), "H_20": m.H.copy(), "ferr_20": m.ferr.copy()}
+    assert out["ferr_20"][-1] / 53 < 0.1
+    m.factorize(compute_h=False, niter=20)
+    out.update(W_a=m.W.copy(), H_a=m.H.copy(), ferr_a=m.ferr.copy())
+    m.factorize(compute_w=False, niter=20)
+    out.update(W_b=m.W.copy(), H_b=m.H.copy(), ferr_b=m.ferr.copy())
+    m.factorize(compute_err=False, niter=20)
+    out.update(W_c=m.W.copy(), H_c=m.H.copy(), ferr_c=m.ferr.copy())
+    m.factorize(niter=20)
+    out.update(W_d=m.W.copy(), H_d=m.H.copy(), ferr_d=m.ferr.copy())
+    np.savez(os.path.join(OUT, "snmf_ref_test_3x50.npz"), **out)
+    print("snmf ref test: ferr[-1]/53 =", out["ferr_20"][-1] / 53, "lens",
+          [len(out[k_]) for k_ in ("ferr_20", "ferr_a", "ferr_b", "ferr_c", "ferr_d")])
+    for name, c in cases.SNMF_CASES.items():
+        X, W0, H0 = cases.build(name)
+        ferr, nW, nH, snaps = run_steps(refs, X.astype(np.float64), W0, H0, c["k"], c["niter"], set(c["keep"]),
+                                        cls="SNMF")
+        if c.get("store32", False):
+            snaps = {k_: v.astype(np.float32) for k_, v in snaps.items()}
+        np.savez(os.path.join(OUT, "%s.npz" % name), ferr=ferr, normW=nW, normH=nH, **snaps)
+        print(name, "ferr", ferr[0], "->", ferr[-1])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "bnmf":
         main_bnmf()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "snmf":
+        main_snmf()
         sys.exit(0)
     main()

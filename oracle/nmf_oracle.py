@@ -133,6 +133,57 @@ def bnmf_factorize(X, W, H, niter=10, compute_w=True, compute_h=True, compute_er
 
 
 # --------------------------------------------------------------------------
+# SNMF (pymf/snmf.py): semi-NMF - X and W signed, H >= 0.  Pinned by tests/golden/snmf_*.npz.
+# --------------------------------------------------------------------------
+def snmf_update_w(X, W, H):
+    """Returns the NEW W (the reference rebinds self.W).  pymf/snmf.py:67-70."""
+    W1 = np.dot(X, H.T)                                     # :68
+    W2 = np.dot(H, H.T)                                     # :69
+    return np.dot(W1, np.linalg.inv(W2))                    # :70
+
+
+def snmf_update_h(X, W, H):
+    """In-place H update.  pymf/snmf.py:72-90."""
+    def separate_positive(m):                               # :73-74
+        return (np.abs(m) + m) / 2.0
+
+    def separate_negative(m):                               # :76-77
+        return (np.abs(m) - m) / 2.0
+
+    XW = np.dot(X.T, W)                                     # :79
+    WW = np.dot(W.T, W)                                     # :81
+    WW_pos = separate_positive(WW)                          # :82
+    WW_neg = separate_negative(WW)                          # :83
+    XW_pos = separate_positive(XW)                          # :85
+    H1 = (XW_pos + np.dot(H.T, WW_neg)).T                   # :86
+    XW_neg = separate_negative(XW)                          # :88
+    H2 = (XW_neg + np.dot(H.T, WW_pos)).T + EPS_DENOM       # :89
+    H *= np.sqrt(H1 / H2)                                   # :90
+    return H
+
+
+def snmf_factorize(X, W, H, niter=1, compute_w=True, compute_h=True, compute_err=True,
+                   early_stop=True, record=None):
+    """NMF.factorize's loop (pymf/nmf.py:182-202) over SNMF's hooks.  Returns (W, ferr): W is
+    rebound by update_w, H is updated in place."""
+    ferr = np.zeros(niter) if compute_err else None
+    for i in range(niter):
+        if compute_w:
+            W = snmf_update_w(X, W, H)
+        if compute_h:
+            snmf_update_h(X, W, H)
+        if compute_err:
+            ferr[i] = frobenius_norm(X, W, H)
+        if record is not None:
+            record(i, W, H, ferr[i] if compute_err else None)
+        if early_stop and i > 1 and compute_err:
+            if converged(ferr, i, X.shape[1]):
+                ferr = ferr[:i]
+                break
+    return W, ferr
+
+
+# --------------------------------------------------------------------------
 # Synthetic inputs shared by tests, smoke() and bench.py (SURVEY.md section 8d).
 # The device generator in pymf_b200/csrc/pymfb.cu (k_gen_uniform) implements the
 # same integer hash so that any shard / tile regenerates bit-identically.

@@ -32,24 +32,36 @@ def load_reference_nmf():
     return mod
 
 
-def load_reference_bnmf():
-    """Returns the reference's pymf/bnmf.py module (with .BNMF) or None.  bnmf.py does
-    ``from .nmf import NMF`` (:18), so it is loaded as a submodule of a synthetic, empty
-    package whose ``nmf`` member is the by-path module above - pymf/__init__.py (which
-    needs cvxopt) is never executed, and nothing is copied or edited."""
+def load_reference_submodule(name):
+    """Returns the reference's pymf/<name>.py module (bnmf, snmf) or None.  These files do
+    ``from .nmf import NMF``, so they are loaded as submodules of a synthetic, empty package whose
+    ``nmf`` member is the by-path module above - pymf/__init__.py (which needs cvxopt) is never
+    executed, and nothing is copied or edited."""
     import sys
     import types
-    nmf = load_reference_nmf()
-    if nmf is None:
-        return None
     pkg_name = "_pymf_ref_pkg"
-    pkg_dir = os.path.dirname(find_reference())
-    pkg = types.ModuleType(pkg_name)
-    pkg.__path__ = [pkg_dir]
-    sys.modules[pkg_name] = pkg
-    sys.modules[pkg_name + ".nmf"] = nmf
-    spec = importlib.util.spec_from_file_location(pkg_name + ".bnmf", os.path.join(pkg_dir, "bnmf.py"))
+    if pkg_name + ".nmf" not in sys.modules:
+        nmf = load_reference_nmf()
+        if nmf is None:
+            return None
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = [os.path.dirname(find_reference())]
+        sys.modules[pkg_name] = pkg
+        sys.modules[pkg_name + ".nmf"] = nmf
+    full = pkg_name + "." + name
+    if full in sys.modules:
+        return sys.modules[full]
+    pkg_dir = sys.modules[pkg_name].__path__[0]
+    spec = importlib.util.spec_from_file_location(full, os.path.join(pkg_dir, name + ".py"))
     mod = importlib.util.module_from_spec(spec)
-    sys.modules[pkg_name + ".bnmf"] = mod
+    sys.modules[full] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_bnmf():
+    return load_reference_submodule("bnmf")
+
+
+def load_reference_snmf():
+    return load_reference_submodule("snmf")

@@ -19,6 +19,7 @@ OPT_PATH = 1
 OPT_ERR_MODE = 2
 OPT_GRAPH = 3
 GRAPH_AUTO, GRAPH_OFF, GRAPH_ON = 0, 1, 2
+VARIANT_NMF, VARIANT_SNMF = 0, 1
 ERR_AUTO, ERR_TRACE, ERR_DIRECT = 0, 1, 2
 
 _c_ctx = C.c_void_p
@@ -33,6 +34,7 @@ SIGNATURES = {
     "pymfb_destroy": (C.c_int, [_c_ctx]),
     "pymfb_set_option": (C.c_int, [_c_ctx, C.c_int, _i64]),
     "pymfb_set_penalty": (C.c_int, [_c_ctx, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "pymfb_set_variant": (C.c_int, [_c_ctx, C.c_int]),
     "pymfb_get_penalty": (C.c_int, [_c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pymfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pymfb_comm_init": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int]),

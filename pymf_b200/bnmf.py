@@ -42,11 +42,9 @@ class BNMF(NMF):
     def update_w(self):                                                 # pymf/bnmf.py:86-89
         NMF.update_w(self)
 
-    def _hooks_overridden(self):
-        cls = type(self)
-        return any(getattr(cls, h) is not getattr(base, h)
-                   for h, base in (("update_w", BNMF), ("update_h", BNMF),
-                                   ("frobenius_norm", NMF), ("converged", NMF)))
+    @staticmethod
+    def _native_hooks():
+        return BNMF
 
     def factorize(self, niter=10, compute_w=True, compute_h=True,
                   show_progress=False, compute_err=True):

@@ -36,6 +36,14 @@ __device__ __forceinline__ float mu_ratio(float v, float num, float den, float l
     return v * ((num + 3.f * lam * v2) / (den + 2.f * lam * (v2 * v) + lam * v + kEpsDenom));
 }
 
+// Semi-NMF H ratio (pymf/snmf.py:72-90): c = (W^T X)[j, col] (signed), dp = (G+ H)[j, col], dn = (G- H)[j, col]
+// with G+ = (|G| + G)/2, G- = (|G| - G)/2 (separate_positive / separate_negative, :73-77):
+//   H <- H * sqrt((c+ + dn) / (c- + dp + 1e-9))
+__device__ __forceinline__ float snmf_ratio(float h, float c, float dp, float dn) {
+    const float cp = fmaxf(c, 0.f), cn = fmaxf(-c, 0.f);
+    return h * sqrtf((cp + dn) / (cn + dp + kEpsDenom));
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t idx) {
     // splitmix64 finaliser; identical to oracle/nmf_oracle.py:hash_uniform
     uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;

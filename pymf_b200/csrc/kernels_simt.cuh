@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
                 const float* __restrict__ W, const float* __restrict__ G,
                 const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
-                int64_t d, int64_t n_loc, int kp, float lam) {
+                int64_t d, int64_t n_loc, int kp, float lam, const float* __restrict__ Gneg) {
+    // Gneg != nullptr: Semi-NMF (pymf/snmf.py:72-90) - G is then G+ and Gneg is G-
     if (st->stop) return;
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
@@ -131,6 +132,27 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
     tile_mac<KB>(dd, G, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);    // G H (G symmetric)
 
     const int64_t col = col0 + tx * 4;
+    if (Gneg != nullptr) {                                                // uniform over the launch
+        float dn[TK][4];
+#pragma unroll
+        for (int i = 0; i < TK; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dn[i][j] = 0.f;
+        tile_mac<KB>(dn, Gneg, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);   // G- H
+        if (col >= n_loc) return;
+#pragma unroll
+        for (int i = 0; i < TK; ++i) {
+            const int krow = kb0 + ty * TK + i;
+            const float4 h = *reinterpret_cast<const float4*>(Hc + (int64_t)krow * ldh + col);
+            float4 o;
+            o.x = snmf_ratio(h.x, c[i][0], dd[i][0], dn[i][0]);
+            o.y = (col + 1 < n_loc) ? snmf_ratio(h.y, c[i][1], dd[i][1], dn[i][1]) : 0.f;
+            o.z = (col + 2 < n_loc) ? snmf_ratio(h.z, c[i][2], dd[i][2], dn[i][2]) : 0.f;
+            o.w = (col + 3 < n_loc) ? snmf_ratio(h.w, c[i][3], dd[i][3], dn[i][3]) : 0.f;
+            *reinterpret_cast<float4*>(Hn + (int64_t)krow * ldh + col) = o;
+        }
+        return;
+    }
     if (col >= n_loc) return;
 #pragma unroll
     for (int i = 0; i < TK; ++i) {
@@ -275,6 +297,131 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
 #pragma unroll
             for (int j = 0; j < TK; ++j) atomicAdd(P + r * ldp + kb0 + tk * TK + j, acc[i][j]);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Semi-NMF helpers (pymf/snmf.py:67-90).
+// ---------------------------------------------------------------------------------------
+// G+ = (|G| + G)/2, G- = (|G| - G)/2                                            (:73-77, applied to W^T W, :81-83)
+__global__ void k_split_posneg(const DevState* __restrict__ st, const float* __restrict__ G, int64_t cnt,
+                               float* __restrict__ Gpos, float* __restrict__ Gneg) {
+    if (st->stop) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) { const float g = G[i]; Gpos[i] = fmaxf(g, 0.f); Gneg[i] = fmaxf(-g, 0.f); }
+}
+
+// Dp = G+ H, Dn = G- H (kp x n_loc each) for the tensor-core H-update kernels, whose epilogue reads them
+// instead of their own G H accumulator in Semi-NMF mode.  Same tiling as k_h_update_simt.
+template <int KB>
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_gh_posneg_simt(const DevState* __restrict__ st, const float* __restrict__ Gpos, const float* __restrict__ Gneg,
+                 const float* __restrict__ Hc, int64_t ldh, int64_t n_loc, int kp,
+                 float* __restrict__ Dp, float* __restrict__ Dn) {
+    if (st->stop) return;
+    constexpr int TK = KB / 8;
+    __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
+    __shared__ __align__(16) float Ls[2][TILE_DK][KB];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * TILE_N;
+    const int kb0 = blockIdx.y * KB;
+    float dp[TK][4], dn[TK][4];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dp[i][j] = 0.f; dn[i][j] = 0.f; }
+    tile_mac<KB>(dp, Gpos, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);
+    tile_mac<KB>(dn, Gneg, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);
+    const int64_t col = col0 + tx * 4;
+    if (col >= n_loc) return;
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+        const int64_t o = (int64_t)(kb0 + ty * TK + i) * ldh + col;
+        *reinterpret_cast<float4*>(Dp + o) = make_float4(dp[i][0], dp[i][1], dp[i][2], dp[i][3]);
+        *reinterpret_cast<float4*>(Dn + o) = make_float4(dn[i][0], dn[i][1], dn[i][2], dn[i][3]);
+    }
+}
+
+// Binv = inverse of the leading k x k block of B = H H^T (row-major, leading dimension kp), fp64 Gauss-Jordan
+// with partial pivoting in ONE CTA (np.linalg.inv of pymf/snmf.py:70 is LU with partial pivoting; k <= 128 here).
+// work: k x 2k doubles [B | I].  A singular B leaves inf / nan in Binv (the reference raises LinAlgError).
+__global__ void __launch_bounds__(256)
+k_inv_f64(const DevState* __restrict__ st, const float* __restrict__ B, int kp, int k,
+          double* __restrict__ work, double* __restrict__ Binv) {
+    if (st->stop) return;
+    const int n2 = 2 * k;
+    __shared__ int s_piv;
+    __shared__ double s_red[256];
+    __shared__ int s_idx[256];
+    for (int f = threadIdx.x; f < k * n2; f += blockDim.x) {
+        const int r = f / n2, c = f % n2;
+        work[f] = c < k ? (double)B[(int64_t)r * kp + c] : (c - k == r ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int p = 0; p < k; ++p) {
+        // pivot search in column p, rows p..k-1
+        double best = -1.0; int bi = p;
+        for (int r = p + threadIdx.x; r < k; r += blockDim.x) {
+            const double v = fabs(work[(int64_t)r * n2 + p]);
+            if (v > best) { best = v; bi = r; }
+        }
+        s_red[threadIdx.x] = best; s_idx[threadIdx.x] = bi;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const double o = s_red[threadIdx.x + s];
+                const int oi = s_idx[threadIdx.x + s];
+                if (o > s_red[threadIdx.x] || (o == s_red[threadIdx.x] && oi < s_idx[threadIdx.x])) {
+                    s_red[threadIdx.x] = o; s_idx[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_piv = s_idx[0];
+        __syncthreads();
+        const int q = s_piv;
+        if (q != p)
+            for (int c = threadIdx.x; c < n2; c += blockDim.x) {
+                const double t = work[(int64_t)p * n2 + c];
+                work[(int64_t)p * n2 + c] = work[(int64_t)q * n2 + c];
+                work[(int64_t)q * n2 + c] = t;
+            }
+        __syncthreads();
+        const double inv = 1.0 / work[(int64_t)p * n2 + p];
+        __syncthreads();
+        for (int c = threadIdx.x; c < n2; c += blockDim.x) work[(int64_t)p * n2 + c] *= inv;
+        __syncthreads();
+        // eliminate column p from every other row; the factors are read before any row is changed
+        for (int f = threadIdx.x; f < k * n2; f += blockDim.x) {
+            const int r = f / n2, c = f % n2;
+            if (r == p || c == p) continue;
+            work[f] -= work[(int64_t)r * n2 + p] * work[(int64_t)p * n2 + c];
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < k; r += blockDim.x)
+            if (r != p) work[(int64_t)r * n2 + p] = 0.0;
+        __syncthreads();
+    }
+    for (int f = threadIdx.x; f < k * k; f += blockDim.x) Binv[f] = work[(int64_t)(f / k) * n2 + k + f % k];
+}
+
+// Semi-NMF W update (pymf/snmf.py:67-70): W = (X H^T) (H H^T)^-1 = A Binv, fp64 accumulation; columns >= k stay 0.
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_update_w_snmf(const DevState* __restrict__ st, const float* __restrict__ A, const double* __restrict__ Binv,
+                float* __restrict__ Wn, int64_t d, int kp, int k) {
+    if (st->stop) return;
+    extern __shared__ float ws[];   // UW_ROWS_S x kp rows of A
+    constexpr int ROWS = 8;
+    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, d - row0);
+    for (int f = threadIdx.x; f < nrows * kp; f += blockDim.x) ws[f] = A[row0 * kp + f];
+    __syncthreads();
+    for (int f = threadIdx.x; f < nrows * kp; f += blockDim.x) {
+        const int r = f / kp, j = f % kp;
+        double s = 0.0;
+        if (j < k)
+            for (int l = 0; l < k; ++l) s = fma((double)ws[r * kp + l], Binv[(int64_t)l * k + j], s);
+        Wn[(row0 + r) * kp + j] = (float)s;
     }
 }
 

@@ -226,7 +226,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              int kh_rows, float lam) {
+              int kh_rows, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
     // kh_rows: rows of H contracted for G H (= the padded k of the whole problem).  For k <= 128 it equals KP;
     // for k > 128 the launch handles one 128-wide block of bases: mapH spans all kh_rows rows of H, mapG is the
     // block's [G_hi | G_lo] column slice, and Hc / Hn / Hs point at the block's rows.
@@ -398,7 +398,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(jbase + j0 + j) * ldh + col;
                             const float h = Hc[o];
-                            const float hn = mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, creg[j0 + j], Dp[o], Dn[o]) : mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
                             Hs[hs_index((jbase + j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
@@ -699,7 +699,9 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              float lam) {
+              float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+    // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
+    // as H, written by k_gh_posneg_simt) instead of the G H accumulator
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -916,7 +918,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
                             const float h = hreg[j0 + j];
-                            const float hn = mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, creg[j0 + j], Dp[o], Dn[o]) : mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
                             Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
@@ -1193,6 +1195,8 @@ struct TcPlan {
     bool use_ts = false;             // k <= 64: A operand from TMEM (k_*_ts), else both operands in smem
     int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
+    const float* Dp = nullptr; // Semi-NMF: G+ H and G- H of the H buffer being updated (set by the scheduler), else null
+    const float* Dn = nullptr;
     float lam_h = 0.f;         // BNMF penalty weight of the next H-update launch (0 = plain NMF), set by the scheduler
     std::string err;
 };
@@ -1403,14 +1407,15 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
         const size_t hoff = (size_t)b * p.kpb * p.ldh;
         tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_h, p.mapW_b[b], p.mapH_h[hsrc], p.mapG_b[b], st, p.Hbuf[hsrc] + hoff, Hn + hoff, p.Hs[hsrc ^ 1] + 2 * hoff,
-            p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.lam_h);
+            p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.lam_h,
+            p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr);
     }
 }
 template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = std::min(p.h_tiles, p.sm_count);
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.lam_h);
+        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.lam_h, p.Dp, p.Dn);
 }
 template <int KP>
 inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {

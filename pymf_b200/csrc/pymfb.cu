@@ -181,6 +181,15 @@ struct pymfb_ctx {
     void* stage = nullptr;         // factor transfer staging (factor_stage)
     size_t stage_bytes = 0;
 
+    // Semi-NMF (pymf/snmf.py): variant switch and its buffers (allocated by pymfb_set_variant)
+    int variant = PYMFB_VARIANT_NMF;
+    float* Gpos = nullptr;         // kp x kp   (|G| + G)/2
+    float* Gneg = nullptr;         // kp x kp   (|G| - G)/2
+    float* Dp = nullptr;           // kp x ldh  G+ H  (tensor-core path only)
+    float* Dn = nullptr;           // kp x ldh  G- H
+    double* inv_work = nullptr;    // k x 2k    Gauss-Jordan tableau
+    double* Binv = nullptr;        // k x k     (H H^T)^-1
+
     // CUDA graph of two steady-state iterations (launch-bound problems), see graph_build
     int graph_opt = PYMFB_GRAPH_AUTO;
     cudaGraphExec_t graph_exec = nullptr;
@@ -267,6 +276,11 @@ static int launch_gram_w(pymfb_ctx* c) {
     c->launches += 2;
     CU(cudaGetLastError());
     if (c->path == PYMFB_PATH_TC && tc_after_gram(c->tc, c->st, c->W[c->wcur], c->G, c->stream, &c->launches)) return fail("split kernel launch failed");
+    if (c->variant == PYMFB_VARIANT_SNMF) {
+        k_split_posneg<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->st, c->G, cnt, c->Gpos, c->Gneg);
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
     c->g_valid = true;
     return 0;
 }
@@ -276,6 +290,15 @@ static int launch_update_w(pymfb_ctx* c) {
     const float* B = c->AB + c->d * c->kp;
     unsigned grid = (unsigned)((c->d + UW_ROWS - 1) / UW_ROWS);
     size_t smem = (size_t)UW_ROWS * c->kp * sizeof(float);
+    if (c->variant == PYMFB_VARIANT_SNMF) {      // W = A B^-1 (pymf/snmf.py:67-70); the old W is not an input
+        k_inv_f64<<<1, 256, 0, c->stream>>>(c->st, B, c->kp, c->k, c->inv_work, c->Binv);
+        k_update_w_snmf<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, A, c->Binv, c->W[c->wcur ^ 1], c->d, c->kp, c->k);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        c->wcur ^= 1;
+        c->g_valid = false;
+        return 0;
+    }
     k_update_w<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, c->W[c->wcur], A, B, c->W[c->wcur ^ 1], c->d, c->kp, (float)c->lam_w);
     c->launches += 1;
     CU(cudaGetLastError());
@@ -288,19 +311,29 @@ static int launch_update_w(pymfb_ctx* c) {
 static int launch_h_update(pymfb_ctx* c) {
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 0, &e0, &e1));
+    const bool snmf = c->variant == PYMFB_VARIANT_SNMF;
     if (c->path == PYMFB_PATH_TC) {
         c->tc.lam_h = (float)c->lam_h;
+        c->tc.Dp = c->tc.Dn = nullptr;
+        if (snmf) {                                // G+ H and G- H of the old H for the epilogue
+            dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
+            k_gh_posneg_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->Gpos, c->Gneg, c->H[c->hcur], c->ldh,
+                                                                       c->n_loc, c->kp, c->Dp, c->Dn);
+            c->launches += 1;
+            CU(cudaGetLastError());
+            c->tc.Dp = c->Dp; c->tc.Dn = c->Dn;
+        }
         if (tc_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("tcgen05 H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
         if (c->kb == 16)
-            k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
+            k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr);
         else
-            k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], c->G,
+            k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr);
         c->launches += 1;
         CU(cudaGetLastError());
     }
@@ -432,7 +465,7 @@ static int enqueue_one(pymfb_ctx* c, bool do_w, bool do_h, bool do_e, bool trace
         if (!c->g_valid) CK(launch_gram_w(c));
         // A, B of the new H feed the next W update and this iteration's error
         const bool need_ab = trace || (do_w && more_after);
-        if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready && c->lam_h == 0.0) {
+        if (need_ab && c->path == PYMFB_PATH_TC && c->fused.ready && c->lam_h == 0.0 && c->variant == PYMFB_VARIANT_NMF) {
             CK(launch_fused(c));
         } else {
             CK(launch_h_update(c));
@@ -610,6 +643,7 @@ int pymfb_destroy(pymfb_ctx* c) {
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->AB != c->P) cudaFree(c->AB);
     cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
+    cudaFree(c->Gpos); cudaFree(c->Gneg); cudaFree(c->Dp); cudaFree(c->Dn); cudaFree(c->inv_work); cudaFree(c->Binv);
     cudaFree(c->stage); cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
     for (int i = 0; i < 2; ++i) { cudaFree(c->W[i]); cudaFree(c->H[i]); }
     cudaStreamDestroy(c->stream);
@@ -656,6 +690,27 @@ int pymfb_set_penalty(pymfb_ctx* c, double lamb_w, double lamb_h, double increas
     c->lam_w = lamb_w; c->lam_h = lamb_h; c->inc_w = increase_w; c->inc_h = increase_h;
     return 0;
 }
+int pymfb_set_variant(pymfb_ctx* c, int variant) {
+    if (!c) return fail("null context");
+    if (variant != PYMFB_VARIANT_NMF && variant != PYMFB_VARIANT_SNMF) return fail("unknown variant %d", variant);
+    CU(cudaSetDevice(c->device));
+    graph_drop(c); c->graph_key = 0;
+    if (variant == PYMFB_VARIANT_SNMF) {
+        if (c->k > 128) return fail("Semi-NMF supports k <= 128 (the k x k inverse runs in one CTA); got k = %d", c->k);
+        if (!c->Gpos) {
+            const size_t gb = (size_t)c->kp * c->kp * sizeof(float), hb = (size_t)c->kp * c->ldh * sizeof(float);
+            CU(cudaMalloc(&c->Gpos, gb)); CU(cudaMalloc(&c->Gneg, gb));
+            CU(cudaMalloc(&c->Dp, hb)); CU(cudaMalloc(&c->Dn, hb));
+            CU(cudaMemsetAsync(c->Dp, 0, hb, c->stream)); CU(cudaMemsetAsync(c->Dn, 0, hb, c->stream));
+            CU(cudaMalloc(&c->inv_work, sizeof(double) * 2 * c->k * c->k));
+            CU(cudaMalloc(&c->Binv, sizeof(double) * c->k * c->k));
+        }
+    }
+    if (variant != c->variant) c->g_valid = false;   // G+ / G- follow the Gram kernel
+    c->variant = variant;
+    return 0;
+}
+
 int pymfb_get_penalty(pymfb_ctx* c, double* lamb_w, double* lamb_h) {
     if (!c) return fail("null context");
     if (lamb_w) *lamb_w = c->lam_w;

@@ -99,6 +99,11 @@ class Engine(object):
     def graph_replays(self):
         return int(self._lib.pymfb_graph_replays(self._ctx))
 
+    def set_variant(self, variant):
+        """'nmf' | 'snmf': which update rules the loop applies (pymf/nmf.py:122-132 / pymf/snmf.py:67-90)."""
+        code = {"nmf": _lib.VARIANT_NMF, "snmf": _lib.VARIANT_SNMF}.get(variant, variant)
+        _lib.check(self._lib.pymfb_set_variant(self._ctx, int(code)))
+
     def set_penalty(self, lamb_w, lamb_h, increase_w=1.0, increase_h=1.0):
         """BNMF penalty weights of the next iteration and their growth per H update (pymf/bnmf.py:70-90)."""
         _lib.check(self._lib.pymfb_set_penalty(self._ctx, float(lamb_w), float(lamb_h),

@@ -69,6 +69,7 @@ class NMF(object):
 
     _EPS = 10 ** -8                      # pymf/nmf.py:69
     _engine_factory = Engine             # tests substitute a checker-backed double here
+    _variant = "nmf"                     # update rules the engine applies (subclasses: "snmf")
 
     def __init__(self, data, num_bases=4, **kw):
         device = kw.pop("device", None)
@@ -169,6 +170,8 @@ class NMF(object):
                 dist.broadcast_object_list(box, src=dist.get_global_rank(self._group(), 0)
                                            if self._group() is not None else 0, group=self._group())
                 self._engine.comm_init(box[0], self._world, self._rank)
+            if self._variant != "nmf":
+                self._engine.set_variant(self._variant)
         if not self._x_uploaded:
             self._upload_data()
             self._x_uploaded = True
@@ -237,9 +240,17 @@ class NMF(object):
         return bool(derr < self._EPS)
 
     def _hooks_overridden(self):
+        """True when a subclass replaced a hook with Python code of its own.  ``_native_hooks`` names the
+        class whose update_w / update_h run natively (NMF, or BNMF / SNMF for their own overrides)."""
         cls = type(self)
-        return any(getattr(cls, h) is not getattr(NMF, h)
-                   for h in ("update_w", "update_h", "frobenius_norm", "converged"))
+        native = self._native_hooks()
+        return any(getattr(cls, h) is not getattr(base, h)
+                   for h, base in (("update_w", native), ("update_h", native),
+                                   ("frobenius_norm", NMF), ("converged", NMF)))
+
+    @staticmethod
+    def _native_hooks():
+        return NMF
 
     # ------------------------------------------------------------------ the driver
     def factorize(self, niter=1, show_progress=False,

@@ -19,6 +19,7 @@ class FakeEngine(object):
         self.uploads = {"x": 0, "w": 0, "h": 0}
         self.lam = {"W": 0.0, "H": 0.0}
         self.inc = (1.0, 1.0)
+        self.variant = "nmf"
 
     # comm -------------------------------------------------------------------------------
     @staticmethod
@@ -40,6 +41,9 @@ class FakeEngine(object):
     def set_penalty(self, lamb_w, lamb_h, increase_w=1.0, increase_h=1.0):
         self.lam = {"W": float(lamb_w), "H": float(lamb_h)}
         self.inc = (float(increase_w), float(increase_h))
+
+    def set_variant(self, variant):
+        self.variant = variant
 
     def get_penalty(self):
         return self.lam["W"], self.lam["H"]
@@ -75,7 +79,9 @@ class FakeEngine(object):
         done = 0
         nf = niter if compute_err else 0
         for i in range(niter):
-            if compute_w:
+            if compute_w and self.variant == "snmf":
+                self.W = O.snmf_update_w(self.X, self.W, self.H)
+            elif compute_w:
                 if self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
                     O.bnmf_update_w(self.X, self.W, self.H, self.lam)
                 elif self.world == 1:
@@ -86,7 +92,9 @@ class FakeEngine(object):
                     W2 = self.W.dot(B) + O.EPS_DENOM
                     self.W *= A
                     self.W /= W2
-            if compute_h:
+            if compute_h and self.variant == "snmf":
+                O.snmf_update_h(self.X, self.W, self.H)
+            elif compute_h:
                 if self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
                     assert self.inc == (O.LAMB_INCREASE_W, O.LAMB_INCREASE_H)
                     O.bnmf_update_h(self.X, self.W, self.H, self.lam)
