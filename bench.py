@@ -42,6 +42,12 @@ WORKLOADS = {
     "cfg4k512": (8192, 524288, 512, "cfg4: 8192x524288, k=512"),
     "cfg5": (32768, 524288, 64, "cfg5: 32768x524288 per GPU (64 GiB), k=64, weak scaling"),
 }
+# --mode: which of factorize()'s flag combinations a step is (tests/test_pymf.py:92-95 of the reference)
+MODES = {
+    "full": dict(compute_w=True, compute_h=True, compute_err=True),        # the BASELINE metric
+    "h_only": dict(compute_w=False, compute_h=True, compute_err=False),    # projection on a fixed basis: one pass over X
+    "w_only": dict(compute_w=True, compute_h=False, compute_err=True),     # H fixed: A, B are loop invariant, no pass over X
+}
 METRIC = "NMF MU iterations/sec"
 UNIT = "iterations/s"
 
@@ -219,7 +225,8 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     eng.sync()
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    eng.enqueue(warmup)
+    mode_kw = MODES[args.mode]
+    eng.enqueue(warmup, **mode_kw)
     eng.sync()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -233,7 +240,7 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     e0, e1 = eng.event(), eng.event()
     barrier()
     eng.record(e0)
-    eng.enqueue(steps)
+    eng.enqueue(steps, **mode_kw)
     eng.record(e1)
     eng.sync()
     barrier()
@@ -254,7 +261,11 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     # ---- roofline of the streaming pass: bytes_alg = 4 d n_loc + 8 k n_loc per iteration
     hbm_peak, bf16_peak, peak_kind = measured_peaks()
     bytes_alg = 4.0 * d * n_loc + 8.0 * k * n_loc
+    if args.mode == "w_only":
+        bytes_alg = 0.0                            # no streaming pass at all
     flops_alg = 4.0 * d * n_loc * k + 4.0 * n_loc * k * k + 4.0 * d * k * k
+    if args.mode == "h_only":
+        flops_alg = 2.0 * d * n_loc * k + 2.0 * n_loc * k * k      # W^T X and G H only
     t_stream_ms = t_h + t_x
     if small:                                     # no per-kernel events: the whole iteration is the unit
         t_stream_ms = ms_per_step
@@ -283,7 +294,7 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
 
     # ---- e2e: pymf_b200.NMF with host buffers (upload + K iterations + download in the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.mode == "full":
         rng = np.random.default_rng(1234 + rank)
         if args.e2e_source == "pinned":          # page-locked host buffers (the contract's e2e source)
             Xh = pymf_b200.pinned_empty((d, n_loc), np.float32)
@@ -329,7 +340,6 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
                "host_source": args.e2e_source, "x_upload_direct_dma": direct,
                "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download; second of two "
                        "identical calls in this process" % steps}
-        del m
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -344,7 +354,7 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl_desc + (" per GPU, n_global = %d" % n_global if not strong else ""),
-                       "d": d, "n_local": n_loc, "n_global": n_global, "k": k, "kernel_path": path,
+                       "mode": args.mode, "d": d, "n_local": n_loc, "n_global": n_global, "k": k, "kernel_path": path,
                        "arithmetic": "fp32 storage; 3xTF32 tcgen05 products (tc path) or fp32 FMA (simt path); fp64 error combine",
                        "l2": "inputs larger than L2 (X shard = %.2f GiB), no flush needed" % (4.0 * d * n_loc / 2 ** 30),
                        "value_units": "shard-iterations/s summed over ranks" if not strong else "iterations/s of the global problem",
@@ -365,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default=None, choices=[None, "auto", "simt", "tc"])
+    ap.add_argument("--mode", default="full", choices=sorted(MODES),
+                    help="full = W, H and error every step (the BASELINE metric); h_only / w_only = serving modes")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-source", default="pinned", choices=["pinned", "pageable"],
                     help="host memory the e2e leg reads X/W/H from (default: page-locked)")
