@@ -79,19 +79,28 @@ class FakeEngine(object):
         done = 0
         nf = niter if compute_err else 0
         for i in range(niter):
-            if compute_w and self.variant == "snmf":
+            if compute_w and self.world > 1:
+                # sharded columns: only the d x k / k x k partials are summed over ranks
+                A = self._allreduce(self.X.dot(self.H.T))
+                B = self._allreduce(self.H.dot(self.H.T))
+                if self.variant == "snmf":
+                    self.W = A.dot(np.linalg.inv(B))
+                elif self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
+                    lw = self.lam["W"]
+                    W1 = A + 3.0 * lw * (self.W ** 2)
+                    W2 = self.W.dot(B) + 2.0 * lw * (self.W ** 3) + lw * self.W + O.EPS_DENOM
+                    self.W *= W1 / W2
+                else:
+                    W2 = self.W.dot(B) + O.EPS_DENOM
+                    self.W *= A
+                    self.W /= W2
+            elif compute_w and self.variant == "snmf":
                 self.W = O.snmf_update_w(self.X, self.W, self.H)
             elif compute_w:
                 if self.lam["W"] != 0.0 or self.lam["H"] != 0.0:
                     O.bnmf_update_w(self.X, self.W, self.H, self.lam)
-                elif self.world == 1:
-                    O.update_w(self.X, self.W, self.H)
                 else:
-                    A = self._allreduce(self.X.dot(self.H.T))
-                    B = self._allreduce(self.H.dot(self.H.T))
-                    W2 = self.W.dot(B) + O.EPS_DENOM
-                    self.W *= A
-                    self.W /= W2
+                    O.update_w(self.X, self.W, self.H)
             if compute_h and self.variant == "snmf":
                 O.snmf_update_h(self.X, self.W, self.H)
             elif compute_h:

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, d, n, k, niter, out):
+def _worker(rank, world, port, d, n, k, niter, out, cls="NMF"):
     import torch.distributed as dist
     import pymf_b200
     from tests._fake_engine import FakeEngine
@@ -32,7 +32,7 @@ def _worker(rank, world, port, d, n, k, niter, out):
         bounds = [int(round(n * r / float(world))) for r in range(world + 1)]
         lo, hi = bounds[rank], bounds[rank + 1]
         np.random.seed(9)                                   # same stream on every rank
-        m = pymf_b200.NMF(X[:, lo:hi], num_bases=k, process_group=True)
+        m = getattr(pymf_b200, cls)(X[:, lo:hi], num_bases=k, process_group=True)
         assert m._num_samples == n and m._col0 == lo
         m.factorize(niter=niter)
         np.savez(os.path.join(out, "r%d.npz" % rank), W=m.W, H=m.H, ferr=m.ferr, lo=lo, hi=hi)
@@ -54,3 +54,23 @@ def test_two_rank_column_sharding_matches_single_process(tmp_path, n):
         np.testing.assert_allclose(p["H"], H[:, int(p["lo"]):int(p["hi"])], rtol=1e-9)
         np.testing.assert_allclose(p["ferr"], ferr, rtol=1e-9)          # global error
     np.testing.assert_array_equal(parts[0]["W"], parts[1]["W"])         # bit-identical replicas
+
+
+@pytest.mark.parametrize("cls", ["BNMF", "SNMF"])
+def test_two_rank_column_sharding_of_the_variants(tmp_path, cls):
+    """BNMF / SNMF shard exactly like NMF: their W updates consume the same summed X H^T / H H^T partials."""
+    d, n, k, niter, world = 17, 101, 4, 9, 2
+    mp.spawn(_worker, args=(world, _free_port(), d, n, k, niter, str(tmp_path), cls), nprocs=world, join=True)
+    X = np.random.RandomState(42).random_sample((d, n))
+    np.random.seed(9)
+    W, H = O.init_wh(d, n, k)
+    if cls == "BNMF":
+        ferr = O.bnmf_factorize(X, W, H, niter=niter)
+    else:
+        W, ferr = O.snmf_factorize(X, W, H, niter=niter)
+    parts = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(world)]
+    for p in parts:
+        np.testing.assert_allclose(p["W"], W, rtol=1e-8)
+        np.testing.assert_allclose(p["H"], H[:, int(p["lo"]):int(p["hi"])], rtol=1e-8, atol=1e-300)
+        np.testing.assert_allclose(p["ferr"], ferr, rtol=1e-9)
+    np.testing.assert_array_equal(parts[0]["W"], parts[1]["W"])

@@ -26,7 +26,7 @@ X = O.gen_matrix(21, d, n)
 bounds = [int(round(n * r / float(world))) for r in range(world + 1)]
 lo, hi = bounds[rank], bounds[rank + 1]
 np.random.seed(5)
-m = pymf_b200.NMF(np.ascontiguousarray(X[:, lo:hi]), num_bases=k, process_group=True, device=rank, path=%(path)r)
+m = getattr(pymf_b200, %(cls)r)(np.ascontiguousarray(X[:, lo:hi]), num_bases=k, process_group=True, device=rank, path=%(path)r)
 m.factorize(niter=niter)
 np.savez(os.path.join(%(out)r, "r%%d.npz" %% rank), W=m.W, H=m.H, ferr=m.ferr, lo=lo, hi=hi)
 dist.destroy_process_group()
@@ -37,15 +37,17 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("shape,path", [((512, 1000, 32), "tc"), ((300, 777, 10), "simt"), ((1024, 4096, 128), "tc")])
-def test_two_gpus_match_oracle(tmp_path, shape, path):
+@pytest.mark.parametrize("shape,path,cls", [((512, 1000, 32), "tc", "NMF"), ((300, 777, 10), "simt", "NMF"),
+                                            ((1024, 4096, 128), "tc", "NMF"), ((512, 1000, 32), "tc", "BNMF"),
+                                            ((512, 1000, 32), "tc", "SNMF"), ((300, 777, 10), "simt", "SNMF")])
+def test_two_gpus_match_oracle(tmp_path, shape, path, cls):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     d, n, k = shape
     niter = 6
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % dict(root=ROOT, d=d, n=n, k=k, niter=niter, out=str(tmp_path), path=path))
+    script.write_text(WORKER % dict(root=ROOT, d=d, n=n, k=k, niter=niter, out=str(tmp_path), path=path, cls=cls))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
@@ -54,7 +56,12 @@ def test_two_gpus_match_oracle(tmp_path, shape, path):
     X = O.gen_matrix(21, d, n).astype(np.float64)
     np.random.seed(5)
     W, H = O.init_wh(d, n, k)
-    ferr = O.factorize(X, W, H, niter=niter)
+    if cls == "BNMF":
+        ferr = O.bnmf_factorize(X, W, H, niter=niter)
+    elif cls == "SNMF":
+        W, ferr = O.snmf_factorize(X, W, H, niter=niter)
+    else:
+        ferr = O.factorize(X, W, H, niter=niter)
     parts = [np.load(str(tmp_path / ("r%d.npz" % r_))) for r_ in range(2)]
 
     def rel(a, b):
