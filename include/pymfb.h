@@ -118,6 +118,17 @@ int pymfb_comm_unique_id(void* out128);
 int pymfb_comm_init(pymfb_ctx* ctx, const void* uid128, int world, int rank);
 
 /*
+ * Shared communicator: creating an NCCL communicator and running its first collective costs
+ * 1-2 s (measured: a fresh NMF object per call paid 1.4 s + 0.7 s at 2 GPUs).  A host layer that
+ * builds several contexts over the same ranks creates the communicator ONCE (comm_create, same
+ * uid hand-shake as comm_init), attaches it to every context (comm_attach: the context borrows
+ * it; contexts sharing one communicator must not run concurrently) and destroys it at exit.
+ */
+int pymfb_comm_create(void** comm_out, int device, const void* uid128, int world, int rank);
+int pymfb_comm_attach(pymfb_ctx* ctx, void* comm, int world, int rank);
+int pymfb_comm_destroy(void* comm);
+
+/*
  * Data residency - replaces `self.data = data` (pymf/nmf.py:93) and the `data[:,:]`
  * full reads (:110,125,131).
  *   bind_x    borrow a device pointer (fp32, row-major, leading dimension ld elements,

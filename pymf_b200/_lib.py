@@ -38,6 +38,9 @@ SIGNATURES = {
     "pymfb_get_penalty": (C.c_int, [_c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pymfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pymfb_comm_init": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int]),
+    "pymfb_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "pymfb_comm_attach": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int]),
+    "pymfb_comm_destroy": (C.c_int, [C.c_void_p]),
     "pymfb_bind_x": (C.c_int, [_c_ctx, C.c_void_p, _i64]),
     "pymfb_upload_x": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, _i64]),
     "pymfb_gen_x": (C.c_int, [_c_ctx, C.c_uint64]),

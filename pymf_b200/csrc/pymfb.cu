@@ -174,6 +174,7 @@ struct pymfb_ctx {
     FusedPlan fused;               // one-pass kernel plan (kernels_fused.cuh)
 
     void* comm = nullptr;
+    bool comm_owned = true;        // false: attached by pymfb_comm_attach, the caller destroys it
     int world = 1, rank = 0;
 
     int64_t launches = 0;
@@ -635,7 +636,7 @@ int pymfb_destroy(pymfb_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->comm && c->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     graph_drop(c);
     tc_release(c->tc);
     fused_release(c->fused);
@@ -724,6 +725,19 @@ int pymfb_comm_unique_id(void* out128) {
     return 0;
 }
 
+static int comm_bind(pymfb_ctx* c, void* comm, bool owned, int world, int rank) {
+    if (c->comm && c->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->comm = comm; c->comm_owned = owned;
+    c->world = world; c->rank = rank;
+    if (c->AB == c->P) {
+        CU(cudaMalloc(&c->AB, c->ab_count * sizeof(float)));
+        CU(cudaMemset(c->AB, 0, c->ab_count * sizeof(float)));
+    }
+    graph_drop(c); c->graph_key = 0;
+    c->ab_valid = false; c->xx_valid = false;
+    return 0;
+}
+
 int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
     if (!c) return fail("null context");
     if (world < 1 || rank < 0 || rank >= world) return fail("bad world/rank %d/%d", world, rank);
@@ -732,11 +746,33 @@ int pymfb_comm_init(pymfb_ctx* c, const void* uid128, int world, int rank) {
     CU(cudaSetDevice(c->device));
     Uid128 uid;
     memcpy(&uid, uid128, sizeof(uid));
-    NC(g_nccl.CommInitRank(&c->comm, world, uid, rank));
-    c->world = world; c->rank = rank;
-    CU(cudaMalloc(&c->AB, c->ab_count * sizeof(float)));
-    CU(cudaMemset(c->AB, 0, c->ab_count * sizeof(float)));
-    c->ab_valid = false; c->xx_valid = false;
+    void* comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+    return comm_bind(c, comm, true, world, rank);
+}
+
+int pymfb_comm_create(void** comm_out, int device, const void* uid128, int world, int rank) {
+    if (!comm_out) return fail("comm_out is null");
+    *comm_out = nullptr;
+    if (world < 2 || rank < 0 || rank >= world) return fail("bad world/rank %d/%d", world, rank);
+    CK(nccl_load());
+    CU(cudaSetDevice(device));
+    Uid128 uid;
+    memcpy(&uid, uid128, sizeof(uid));
+    NC(g_nccl.CommInitRank(comm_out, world, uid, rank));
+    return 0;
+}
+
+int pymfb_comm_attach(pymfb_ctx* c, void* comm, int world, int rank) {
+    if (!c) return fail("null context");
+    if (!comm) return fail("comm is null");
+    if (world < 2 || rank < 0 || rank >= world) return fail("bad world/rank %d/%d", world, rank);
+    CU(cudaSetDevice(c->device));
+    return comm_bind(c, comm, false, world, rank);
+}
+
+int pymfb_comm_destroy(void* comm) {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     return 0;
 }
 

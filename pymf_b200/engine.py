@@ -128,6 +128,18 @@ class Engine(object):
         buf = C.create_string_buffer(bytes(uid), 128)
         _lib.check(self._lib.pymfb_comm_init(self._ctx, buf, int(world), int(rank)))
 
+    @staticmethod
+    def comm_create(uid, world, rank, device):
+        """A communicator that outlives engines (pymfb_comm_create); attach it with comm_attach."""
+        buf = C.create_string_buffer(bytes(uid), 128)
+        comm = C.c_void_p()
+        _lib.check(_lib.load().pymfb_comm_create(C.byref(comm), int(device), buf, int(world), int(rank)))
+        return comm
+
+    def comm_attach(self, comm, world, rank):
+        self._comm_keepalive = comm
+        _lib.check(self._lib.pymfb_comm_attach(self._ctx, comm, int(world), int(rank)))
+
     # -- data -----------------------------------------------------------------------------
     def upload_x(self, x):
         """x: host array (d x n_local), float32 or float64, last axis contiguous."""

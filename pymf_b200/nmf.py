@@ -122,6 +122,32 @@ class NMF(object):
         self._n_global = int(sum(sizes))
         self._col0 = int(sum(sizes[:self._rank]))
 
+    # NCCL communicators are created once per (process group, device) and shared by every NMF object of this
+    # process (creating one and warming it up costs 1-2 s; all ranks construct their objects in the same order,
+    # so the cache stays in step across ranks).
+    _comm_cache = {}
+
+    def _attach_comm(self):
+        eng = self._engine
+        if not hasattr(eng, "comm_attach"):                    # engine doubles of the CPU tests
+            box = [eng.comm_unique_id() if self._rank == 0 else None]
+            self._broadcast(box)
+            eng.comm_init(box[0], self._world, self._rank)
+            return
+        key = ("WORLD" if self._group() is None else id(self._group()), self._device, self._world, self._rank)
+        comm = NMF._comm_cache.get(key)
+        if comm is None:
+            box = [eng.comm_unique_id() if self._rank == 0 else None]
+            self._broadcast(box)
+            comm = type(eng).comm_create(box[0], self._world, self._rank, self._device)
+            NMF._comm_cache[key] = comm
+        eng.comm_attach(comm, self._world, self._rank)
+
+    def _broadcast(self, box):
+        dist = self._dist()
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self._group(), 0)
+                                   if self._group() is not None else 0, group=self._group())
+
     # ------------------------------------------------------------------ attributes
     @property
     def data(self):
@@ -165,11 +191,7 @@ class NMF(object):
                                                 device=self._device, n_global=self._num_samples,
                                                 col0=self._col0, path=self._path)
             if self._world > 1:
-                dist = self._dist()
-                box = [self._engine.comm_unique_id() if self._rank == 0 else None]
-                dist.broadcast_object_list(box, src=dist.get_global_rank(self._group(), 0)
-                                           if self._group() is not None else 0, group=self._group())
-                self._engine.comm_init(box[0], self._world, self._rank)
+                self._attach_comm()
             if self._variant != "nmf":
                 self._engine.set_variant(self._variant)
         if not self._x_uploaded:
