@@ -579,9 +579,12 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     if (ndev <= 0) return fail("no CUDA device available: libpymfb has no CPU fallback");
     if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail("device %d is sm_%d%d; libpymfb is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    // single attributes, not cudaGetDeviceProperties (which queries everything and costs milliseconds per call)
+    int cc_major = 0, cc_minor = 0, sm_count = 0;
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major != 10) return fail("device %d is sm_%d%d; libpymfb is built for sm_100a (B200) only", device, cc_major, cc_minor);
     pymfb_ctx* c = new pymfb_ctx();
     c->device = device; c->d = d; c->n_loc = n_local; c->n_glob = n_global; c->col0 = col0; c->k = k;
     // k is zero-padded to kp (exact: padded rows / columns of W and H stay 0 under the updates).  Small k on a
@@ -592,7 +595,7 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     // 128 < k <= 512 on a streaming-sized problem: blocks of 128 bases on the tensor path (kernels_tc.cuh)
     if (k > 128 && k <= 512 && streaming_size) c->kp = (int)round_up(k, 128);
     c->kb = std::min(c->kp, 32);
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = sm_count;
     c->ldh = padded_ld(n_local);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t wbytes = (size_t)d * c->kp * sizeof(float), hbytes = (size_t)c->kp * c->ldh * sizeof(float);
