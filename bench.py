@@ -338,6 +338,7 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
                "seconds_upload": t_up, "seconds_iterations": t_it, "seconds_download": t_dn,
                "first_call_seconds": rec[0][0],
                "host_source": args.e2e_source, "x_upload_direct_dma": direct,
+               "numa": dict(zip(("gpu_node", "x_host_node"), pymf_b200.numa_info(Xh, local_rank))),
                "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download; second of two "
                        "identical calls in this process" % steps}
 

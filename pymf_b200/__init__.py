@@ -7,8 +7,8 @@
 from .nmf import NMF  # noqa: F401
 from .bnmf import BNMF  # noqa: F401
 from .snmf import SNMF  # noqa: F401
-from .engine import Engine, pinned_empty  # noqa: F401
+from .engine import Engine, pinned_empty, numa_info  # noqa: F401
 from ._lib import PymfbError  # noqa: F401
 
-__all__ = ["NMF", "BNMF", "SNMF", "Engine", "PymfbError", "pinned_empty"]
+__all__ = ["NMF", "BNMF", "SNMF", "Engine", "PymfbError", "pinned_empty", "numa_info"]
 __version__ = "0.1.0"

@@ -47,6 +47,8 @@ SIGNATURES = {
     "pymfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pymfb_host_free": (C.c_int, [C.c_void_p]),
     "pymfb_last_upload_pinned": (C.c_int, [_c_ctx]),
+    "pymfb_device_numa_node": (C.c_int, [C.c_int]),
+    "pymfb_host_node_of": (C.c_int, [C.c_void_p]),
     "pymfb_set_w": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),
     "pymfb_set_h": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),
     "pymfb_get_w": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),

@@ -53,6 +53,14 @@ def pinned_empty(shape, dtype=np.float32):
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
+def numa_info(array=None, device=0):
+    """(NUMA node of the GPU, NUMA node holding the first page of `array`), -1 where unknown."""
+    lib = _lib.load()
+    gpu = int(lib.pymfb_device_numa_node(int(device)))
+    host = int(lib.pymfb_host_node_of(C.c_void_p(array.ctypes.data))) if array is not None else -1
+    return gpu, host
+
+
 class Engine(object):
     def __init__(self, d, n_local, k, device=0, n_global=None, col0=0, path=None):
         self._lib = _lib.load()
