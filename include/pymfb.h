@@ -155,9 +155,9 @@ int pymfb_gen_x(pymfb_ctx* ctx, uint64_t seed);
 int pymfb_host_alloc(void** out, size_t bytes);
 int pymfb_host_free(void* ptr);
 int pymfb_last_upload_pinned(pymfb_ctx* ctx);
-/* pymfb_host_alloc places the buffer on the NUMA node of the CURRENT device (mmap + mbind + cudaHostRegister;
- * cudaHostAlloc when that is not possible, or with PYMFB_NO_NUMA set): DMA across sockets ran at 20 GB/s
- * instead of 53.  device_numa_node: node of a device (-1 unknown); host_node_of: node that holds an address. */
+/* pymfb_host_alloc places the buffer on the NUMA node of the CURRENT device when the OS exposes one (mmap +
+ * mbind + cudaHostRegister; plain cudaHostAlloc otherwise, or with PYMFB_NO_NUMA set).
+ * device_numa_node: node of a device (-1 unknown); host_node_of: node that holds an address. */
 int pymfb_device_numa_node(int device);
 int pymfb_host_node_of(const void* ptr);
 

@@ -979,9 +979,10 @@ int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
 int pymfb_last_upload_pinned(pymfb_ctx* c) { return c && c->last_upload_pinned ? 1 : 0; }
 
 // ---- NUMA-aware page-locked host memory ---------------------------------------------------
-// DMA from the socket the GPU is NOT attached to ran at 20 GB/s instead of 53 GB/s on one of the 8-GPU boxes
-// (same code, same sizes), so page-locked buffers are placed on the GPU's own NUMA node: mmap + mbind(preferred
-// node) + cudaHostRegister.  Everything degrades to cudaHostAlloc when /sys or mbind are not available.
+// Page-locked buffers are placed on the GPU's own NUMA node when the OS exposes one: mmap + mbind(preferred node)
+// + cudaHostRegister (DMA across sockets is typically 2-3x slower).  The GPU boxes of this project are single-node
+// VMs (numa_node = -1), where this degrades to plain cudaHostAlloc; the H2D rate there varied between 20 and
+// 53 GB/s from box to box with identical code (VM placement), see DESIGN.md 5.3.
 int pymfb_device_numa_node(int device) {
     char bus[64] = "";
     if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
