@@ -118,6 +118,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same with both descriptors passed as 32-bit halves (see umma_tf32_ts_lh): the high halves are loop invariant.
+__device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t ad_lo, uint32_t ad_hi, uint32_t bd_lo, uint32_t bd_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 ad, {%1, %2};\n\t"
+        "mov.b64 bd, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(ad_lo), "r"(ad_hi), "r"(bd_lo), "r"(bd_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -296,6 +307,13 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 1, 1);
             int s = 0; uint32_t ph = 0; uint32_t g = 0;
+            // descriptors of stage 0 (one MMA, K = 8, = two 4-row swizzle atoms, SBO = 512 B; 32-column chunks LBO apart);
+            // stage s / k-group kg add (s * STAGE_BYTES + kg * 1024) >> 4 to the low words, the high words never change
+            const uint64_t d_hi0 = make_desc(xraw(0), R1 * 128, 512, 1), d_lo0 = make_desc(xlo(0), R1 * 128, 512, 1);
+            const uint64_t d_b0 = make_desc(wch(0), R1 * 128, 512, 1);
+            const uint32_t dh = (uint32_t)(d_hi0 >> 32);      // identical for the three operands (same LBO / SBO / layout)
+            const uint32_t ahi0 = (uint32_t)d_hi0, alo0 = (uint32_t)d_lo0, b0 = (uint32_t)d_b0;
+            uint32_t soff = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
@@ -312,18 +330,16 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         if (elect_one()) {
 #pragma unroll
                             for (int kg = 0; kg < R1 / 8; ++kg) {
-                                // one MMA (K = 8) = two 4-row swizzle atoms (SBO = 512 B); 32-column chunks LBO apart
-                                const uint64_t a_hi = make_desc(xraw(s) + kg * 1024, R1 * 128, 512, 1);
-                                const uint64_t a_lo = make_desc(xlo(s) + kg * 1024, R1 * 128, 512, 1);
-                                const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
-                                umma_tf32(dcol, a_hi, bd, idesc_hl, (first && kg == 0) ? 0u : 1u);
-                                umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                                const uint32_t o = soff + kg * (1024 >> 4);
+                                umma_tf32_lh(dcol, ahi0 + o, dh, b0 + o, dh, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                                umma_tf32_lh(dcol + KP, alo0 + o, dh, b0 + o, dh, idesc_h, 1u);
                             }
                             umma_commit(empty_bar(s));
                         }
                         __syncwarp();
                         first = false;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                        soff += Cfg::STAGE_BYTES >> 4;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
                     }
                     if (elect_one()) umma_commit(tfull_bar(b));
                     __syncwarp();
@@ -507,6 +523,11 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
             int s = 0; uint32_t ph = 0; uint32_t g = 0;
+            // K-major SW128 descriptors of stage 0; stage s / k-step ks add (s * STAGE_BYTES + ks * 32) >> 4 to the low words
+            const uint64_t xd_hi0 = make_desc(xraw(0), 16, 1024), xd_lo0 = make_desc(xlo(0), 16, 1024), xd_b0 = make_desc(hch(0), 16, 1024);
+            const uint32_t xdh = (uint32_t)(xd_hi0 >> 32);
+            const uint32_t xahi0 = (uint32_t)xd_hi0, xalo0 = (uint32_t)xd_lo0, xb0 = (uint32_t)xd_b0;
+            uint32_t soff = 0;
             for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
                 int c_begin;
                 const int nch = task_chunks(task, c_begin);
@@ -525,17 +546,16 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                         if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t a_hi = make_desc(xraw(s) + ks * 32, 16, 1024);
-                                const uint64_t a_lo = make_desc(xlo(s) + ks * 32, 16, 1024);
-                                const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
-                                umma_tf32(dcol, a_hi, bd, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                                umma_tf32(dcol + KP, a_lo, bd, idesc_h, 1u);
+                                const uint32_t o = soff + ks * (32 >> 4);
+                                umma_tf32_lh(dcol, xahi0 + o, xdh, xb0 + o, xdh, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                                umma_tf32_lh(dcol + KP, xalo0 + o, xdh, xb0 + o, xdh, idesc_h, 1u);
                             }
                             umma_commit(empty_bar(s));
                         }
                         __syncwarp();
                         first = false;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                        soff += Cfg::STAGE_BYTES >> 4;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
                     }
                     if (elect_one()) umma_commit(tfull_bar(b));
                     __syncwarp();
@@ -625,6 +645,18 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Same, with the shared-memory descriptor passed as two 32-bit halves: the high half (LBO/SBO/layout bits) is loop
+// invariant and the low half only advances by (byte offset >> 4), so the issue loop does one 32-bit add per
+// descriptor instead of rebuilding it (shift, mask, or) on the uniform datapath for every k-step.
+__device__ __forceinline__ void umma_tf32_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t bd_lo, uint32_t bd_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(bd_lo), "r"(bd_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -772,6 +804,11 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
             int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0; uint32_t mc = 0;
+            // [W_hi|W_lo] / [G_hi|G_lo] operand descriptor of stage 0; stage s, k-group kg add (s * STAGE_BYTES + kg * 1024) >> 4
+            // to the low word (shared-memory addresses are < 2^18, so the 14-bit address field never carries)
+            const uint64_t bd0 = make_desc(wch(0), R1 * 128, 512, 1);
+            const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo0 = (uint32_t)bd0;
+            uint32_t soff = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
@@ -790,14 +827,14 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
                         if (elect_one()) {
+                            const uint32_t bl = bd_lo0 + soff;
 #pragma unroll
                             for (int kg = 0; kg < R1 / 8; ++kg) {
-                                const uint64_t bd = make_desc(wch(s) + kg * 1024, R1 * 128, 512, 1);
                                 const uint32_t dc = dcol + (kg % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
 #if !defined(PYMFB_EXP_SKIP_MMA)
-                                umma_tf32_ts(dc, a_hi + kg * 8, bd, idesc_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
+                                umma_tf32_ts_lh(dc, a_hi + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
 #if !defined(PYMFB_EXP_ONE_MMA)
-                                umma_tf32_ts(dc + KP, a_hi + 32 + kg * 8, bd, idesc_h, 1u);
+                                umma_tf32_ts_lh(dc + KP, a_hi + 32 + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_h, 1u);
 #endif
 #endif
                             }
@@ -807,7 +844,8 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         __syncwarp();
                         TRACE_AT(mc, 7);
                         first = false;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                        soff += Cfg::STAGE_BYTES >> 4;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
                         if (++t == Cfg::NT) { t = 0; tph ^= 1; }
                     }
                     if (elect_one()) umma_commit(tfull_bar(b));
@@ -1019,6 +1057,10 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
         constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
         int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0;
+        // [H_hi;H_lo] operand descriptor of stage 0; stage s / k-step ks add (s * STAGE_BYTES + ks * 32) >> 4 to the low word
+        const uint64_t hd0 = make_desc(hch(0), 16, 1024);
+        const uint32_t hd_hi = (uint32_t)(hd0 >> 32), hd_lo0 = (uint32_t)hd0;
+        uint32_t soff = 0;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
             int c_begin, row0; bool hh;
             const int nch = task_info(task, c_begin, row0, hh);
@@ -1036,19 +1078,20 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     tc_fence_after();
                     const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
                     if (elect_one()) {
+                        const uint32_t bl = hd_lo0 + soff;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t bd = make_desc(hch(s) + ks * 32, 16, 1024);
                             const uint32_t dc = dcol + (ks % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
-                            umma_tf32_ts(dc, a_hi + ks * 8, bd, idesc_hl, (first && ks < Cfg::NCHAIN) ? 0u : 1u);
-                            umma_tf32_ts(dc + KP, a_hi + 32 + ks * 8, bd, idesc_h, 1u);
+                            umma_tf32_ts_lh(dc, a_hi + ks * 8, bl + ks * (32 >> 4), hd_hi, idesc_hl, (first && ks < Cfg::NCHAIN) ? 0u : 1u);
+                            umma_tf32_ts_lh(dc + KP, a_hi + 32 + ks * 8, bl + ks * (32 >> 4), hd_hi, idesc_h, 1u);
                         }
                         umma_commit(empty_bar(s));
                         umma_commit(aempty_bar(t));
                     }
                     __syncwarp();
                     first = false;
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    soff += Cfg::STAGE_BYTES >> 4;
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
                     if (++t == Cfg::NT) { t = 0; tph ^= 1; }
                 }
                 if (elect_one()) umma_commit(tfull_bar(b));
