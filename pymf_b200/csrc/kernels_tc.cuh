@@ -73,11 +73,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __noinline__ void mbar_watchdog(long long t0) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();
+        // the watchdog (out of line) runs only every 256th retry: the retry loop itself stays a handful of
+        // instructions, so a waiter reacts to the phase flip without a clock read + 64-bit compare in between
+        if (((++spins) & 0xFFu) == 0u) mbar_watchdog(t0);
     }
 }
 // One elected lane of a CONVERGED warp.  The producer and MMA warps run their loops with all 32 lanes
@@ -821,7 +827,8 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                     bool first = true;
                     for (; it < seg_end; ++it, ++mc) {
                         TRACE_AT(mc, 5);
-                        mbar_wait(full_bar(s), ph);
+                        // afull(t) implies full(s): the convert warps waited on full(s) - the barrier that also counts the
+                        // [W_hi|W_lo] bytes of the stage - before they filled A slot t and arrived on afull(t)
                         mbar_wait(afull_bar(t), tph);
                         TRACE_AT(mc, 6);
                         tc_fence_after();
@@ -1073,8 +1080,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
                 bool first = true;
                 for (; ch < seg_end; ++ch) {
-                    mbar_wait(full_bar(s), ph);
-                    mbar_wait(afull_bar(t), tph);
+                    mbar_wait(afull_bar(t), tph);       // implies full(s), see k_h_update_ts
                     tc_fence_after();
                     const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
                     if (elect_one()) {
