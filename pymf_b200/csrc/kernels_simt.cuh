@@ -103,21 +103,26 @@ __device__ __forceinline__ void tile_mac(float (&acc)[KB / 8][4],
 
 // ---------------------------------------------------------------------------------------
 // H update pass (pymf/nmf.py:122-126), any shape.
-//   grid.x = column tiles of 128, grid.y = k blocks of KB rows.
+//   grid.x = column tiles of 128, grid.y = k blocks of KB rows, grid.z = splits of the contraction over d.
 //   C = W^T X  (contract over d),  D = G H (contract over kp),  Hn = H * C / (D + 1e-9)
 // Hc is read (all kp rows, for D), Hn is written (rows of this k block) -> ping-pong buffers.
+// Few-column problems (cfg1: n = 500 -> 4 tiles) would run on 4 SMs: with gridDim.z > 1 every CTA contracts
+// rows_per_split rows of X, parks its partial C in Cpart, and the CTA that arrives LAST on the tile's ticket sums
+// the partials in split order (deterministic) and applies the update.  The ticket is reset for the next launch.
 // ---------------------------------------------------------------------------------------
 template <int KB>
 __global__ void __launch_bounds__(SIMT_THREADS)
 k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
                 const float* __restrict__ W, const float* __restrict__ G,
                 const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
-                int64_t d, int64_t n_loc, int kp, float lam, const float* __restrict__ Gneg) {
+                int64_t d, int64_t n_loc, int kp, float lam, const float* __restrict__ Gneg,
+                int64_t rows_per_split, float* __restrict__ Cpart, unsigned* __restrict__ tickets) {
     // Gneg != nullptr: Semi-NMF (pymf/snmf.py:72-90) - G is then G+ and Gneg is G-
     if (st->stop) return;
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
     __shared__ __align__(16) float Ls[2][TILE_DK][KB];
+    __shared__ bool is_last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t col0 = (int64_t)blockIdx.x * TILE_N;
     const int kb0 = blockIdx.y * KB;
@@ -128,7 +133,36 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; dd[i][j] = 0.f; }
 
-    tile_mac<KB>(c, W, kp, kb0, X, ldx, col0, n_loc, 0, d, Rs, Ls);       // W^T X
+    const int nsplit = (int)gridDim.z;
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = nsplit > 1 ? min(d, r_begin + rows_per_split) : d;
+    tile_mac<KB>(c, W, kp, kb0, X, ldx, col0, n_loc, r_begin, r_end, Rs, Ls);       // W^T X (this CTA's rows)
+    if (nsplit > 1) {
+        const int64_t tile_id = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        float* part = Cpart + (tile_id * nsplit) * (KB * TILE_N);                  // [split][KB][TILE_N] of this tile
+        float* mine = part + (int64_t)blockIdx.z * (KB * TILE_N);
+#pragma unroll
+        for (int i = 0; i < TK; ++i)
+            *reinterpret_cast<float4*>(mine + (ty * TK + i) * TILE_N + tx * 4) = make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(&tickets[tile_id], 1u) == (unsigned)(nsplit - 1));
+        __syncthreads();
+        if (!is_last) return;                                                      // block-uniform
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < TK; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+            for (int i = 0; i < TK; ++i) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)sp * (KB * TILE_N) + (ty * TK + i) * TILE_N + tx * 4));
+                c[i][0] += v.x; c[i][1] += v.y; c[i][2] += v.z; c[i][3] += v.w;
+            }
+        }
+        if (threadIdx.x == 0) tickets[tile_id] = 0u;
+    }
     tile_mac<KB>(dd, G, kp, kb0, Hc, ldh, col0, n_loc, 0, kp, Rs, Ls);    // G H (G symmetric)
 
     const int64_t col = col0 + tx * 4;

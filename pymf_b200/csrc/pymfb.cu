@@ -190,6 +190,12 @@ struct pymfb_ctx {
     void* stage = nullptr;         // factor transfer staging (factor_stage)
     size_t stage_bytes = 0;
 
+    // SIMT H-update: splits of the contraction over d when there are few column tiles (k_h_update_simt)
+    int hsplit = 1;
+    int64_t h_rows_per_split = 0;
+    float* h_cpart = nullptr;      // tiles x hsplit x KB x TILE_N partial W^T X
+    unsigned* h_tickets = nullptr; // one arrival counter per (column tile, k block)
+
     // Semi-NMF (pymf/snmf.py): variant switch and its buffers (allocated by pymfb_set_variant)
     int variant = PYMFB_VARIANT_NMF;
     float* Gpos = nullptr;         // kp x kp   (|G| + G)/2
@@ -334,15 +340,17 @@ static int launch_h_update(pymfb_ctx* c) {
         }
         if (tc_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("tcgen05 H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
-        dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb));
+        dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb), (unsigned)c->hsplit);
         if (c->kb == 16)
             k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets);
         else
             k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
-                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr);
+                                                                      c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets);
         c->launches += 1;
         CU(cudaGetLastError());
     }
@@ -636,6 +644,18 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
         const int64_t nb = ((n_local + TILE_N - 1) / TILE_N) * ((d + c->kb - 1) / c->kb);
         CU(cudaMalloc(&c->resid_part, sizeof(double) * nb));
     }
+    {   // SIMT H-update: enough CTAs to cover the SMs, >= 64 rows of X per split
+        const int64_t tiles = ((n_local + TILE_N - 1) / TILE_N) * (c->kp / c->kb);
+        int64_t want = std::max<int64_t>(1, (2LL * c->sm_count) / tiles);
+        want = std::min<int64_t>(want, std::max<int64_t>(1, d / 64));
+        c->h_rows_per_split = round_up((d + want - 1) / want, TILE_DK);
+        c->hsplit = (int)((d + c->h_rows_per_split - 1) / c->h_rows_per_split);
+        if (c->hsplit > 1) {
+            CU(cudaMalloc(&c->h_cpart, (size_t)tiles * c->hsplit * c->kb * TILE_N * sizeof(float)));
+            CU(cudaMalloc(&c->h_tickets, (size_t)tiles * sizeof(unsigned)));
+            CU(cudaMemsetAsync(c->h_tickets, 0, (size_t)tiles * sizeof(unsigned), c->stream));
+        }
+    }
     CU(cudaMalloc(&c->st, sizeof(DevState)));
     CU(cudaMemsetAsync(c->st, 0, sizeof(DevState), c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -655,6 +675,7 @@ int pymfb_destroy(pymfb_ctx* c) {
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->AB != c->P) cudaFree(c->AB);
     cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
+    cudaFree(c->h_cpart); cudaFree(c->h_tickets);
     cudaFree(c->Gpos); cudaFree(c->Gneg); cudaFree(c->Dp); cudaFree(c->Dn); cudaFree(c->inv_work); cudaFree(c->Binv);
     cudaFree(c->stage); cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
     for (int i = 0; i < 2; ++i) { cudaFree(c->W[i]); cudaFree(c->H[i]); }
