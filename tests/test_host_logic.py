@@ -155,3 +155,33 @@ def test_progress_logging(NMF, caplog):
     assert msgs[0].startswith("Iteration 1/2 FN:") and msgs[1].startswith("Iteration 2/2 FN:")
     m.factorize(niter=1)
     assert logging.getLogger("pymf").level == logging.ERROR
+
+
+def test_h5py_style_data_source_is_read_through_full_slice(NMF):
+    """The reference only ever touches `data` through `data[:,:]` and `.shape` (pymf/nmf.py:97,110,125,131 -
+    the h5py convention of the package, pymf/kmeans.py:71); any object offering those two works here too."""
+    reads = []
+
+    class Sliceable(object):
+        def __init__(self, a):
+            self._a = a
+            self.shape = a.shape
+
+        def __getitem__(self, key):
+            reads.append(key)
+            return self._a[key]
+
+    rng = np.random.RandomState(3)
+    X = rng.random_sample((9, 20))
+    W0, H0 = rng.random_sample((9, 3)), rng.random_sample((3, 20))
+    a = NMF(Sliceable(X), num_bases=3)
+    a.W, a.H = W0.copy(), H0.copy()
+    a.factorize(niter=4)
+    b = NMF(X, num_bases=3)
+    b.W, b.H = W0.copy(), H0.copy()
+    b.factorize(niter=4)
+    np.testing.assert_array_equal(a.ferr, b.ferr)
+    np.testing.assert_array_equal(a.W, b.W)
+    assert len(reads) == 1 and reads[0] == (slice(None), slice(None))     # read once, then resident
+    a.factorize(niter=2)
+    assert len(reads) == 1
