@@ -99,7 +99,7 @@ int pymfb_get_penalty(pymfb_ctx* ctx, double* lamb_w, double* lamb_h);
  *   W <- (X H^T) (H H^T)^-1                                                         (:67-70)
  *   H <- H * sqrt(((W^T X)+ + G- H) / ((W^T X)- + G+ H + 1e-9)),  G = W^T W,
  *        m+ = (|m| + m)/2, m- = (|m| - m)/2                                         (:72-90)
- * on the same passes: the X H^T / H H^T reductions feed a fp64 k x k inverse (k <= 128), the
+ * on the same passes: the X H^T / H H^T reductions feed a fp64 k x k inverse (k <= 512, one CTA), the
  * H-update pass keeps its W^T X contraction and switches its epilogue.  Error, early stop, flags
  * and sharding are those of NMF.
  */

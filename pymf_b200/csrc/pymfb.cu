@@ -729,7 +729,7 @@ int pymfb_set_variant(pymfb_ctx* c, int variant) {
     CU(cudaSetDevice(c->device));
     graph_drop(c); c->graph_key = 0;
     if (variant == PYMFB_VARIANT_SNMF) {
-        if (c->k > 128) return fail("Semi-NMF supports k <= 128 (the k x k inverse runs in one CTA); got k = %d", c->k);
+        if (c->k > 512) return fail("Semi-NMF supports k <= 512 (the k x k inverse runs in one CTA); got k = %d", c->k);
         if (!c->Gpos) {
             const size_t gb = (size_t)c->kp * c->kp * sizeof(float), hb = (size_t)c->kp * c->ldh * sizeof(float);
             CU(cudaMalloc(&c->Gpos, gb)); CU(cudaMalloc(&c->Gneg, gb));

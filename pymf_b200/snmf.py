@@ -17,7 +17,7 @@ class SNMF(NMF):
     Semi-NMF: ``|data - W*H|`` minimal with ``H >= 0``.  Drop-in for ``pymf.SNMF``
     (pymf/snmf.py:22): constructor, ``factorize`` and attributes are NMF's; ``update_w`` is
     ``W = X H^T (H H^T)^-1`` (:67-70) and ``update_h`` the square-root ratio of :72-90.
-    ``num_bases`` <= 128 (the k x k inverse runs in one CTA, in float64).
+    ``num_bases`` <= 512 (the k x k inverse runs in one CTA, in float64).
     """
 
     _variant = "snmf"
