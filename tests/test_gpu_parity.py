@@ -402,3 +402,34 @@ def test_graph_replay_keeps_early_stop_semantics(golden_dir):
     # fp32 round-off moves the exact stopping index a little from run to run (atomics); the state must be consistent
     assert abs(out["auto"][0] - out["off"][0]) <= max(5, 0.05 * out["off"][0])
     assert rel(out["auto"][2], out["off"][2]) < 1e-3
+
+
+def test_c_abi_reports_errors_instead_of_crashing():
+    """Error convention of include/pymfb.h: non-zero return + pymfb_last_error(), never an exception or a crash."""
+    import ctypes as C
+    from pymf_b200 import _lib
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    assert lib.pymfb_create(C.byref(ctx), 0, 0, 10, 10, 0, 2) != 0 and b"bad shape" in lib.pymfb_last_error()
+    assert lib.pymfb_create(C.byref(ctx), 99, 8, 8, 8, 0, 2) != 0 and b"out of range" in lib.pymfb_last_error()
+    e = pymf_b200.Engine(16, 200, 3)
+    try:
+        with pytest.raises(pymf_b200.PymfbError, match="no data bound"):
+            e.run(1)
+        e.upload_x(np.random.RandomState(0).random_sample((16, 200)))
+        with pytest.raises(pymf_b200.PymfbError, match="W and H must be set"):
+            e.run(1)
+        with pytest.raises(ValueError):
+            e.set_w(np.zeros((5, 3)))
+        with pytest.raises(pymf_b200.PymfbError, match="tcgen05 path not available"):
+            e.set_path("tc")                       # d = 16 is below the tensor path's minimum
+        e.set_path("auto")
+        with pytest.raises(pymf_b200.PymfbError, match="bad penalty"):
+            e.set_penalty(-1.0, 0.0)
+        assert lib.pymfb_upload_x(e._ctx, None, 0, 200) != 0 and b"null" in lib.pymfb_last_error()
+        e.set_w(np.ones((16, 3))); e.set_h(np.ones((3, 200)))
+        f, done = e.run(2)
+        assert done == 2 and np.all(np.isfinite(f))
+        assert e.run(0)[1] == 0                    # niter = 0 is a no-op
+    finally:
+        e.close()
