@@ -6,7 +6,6 @@ Prints ms/iteration and the fused-kernel time for each (depth, hint); the first 
 baseline.  Parameters are read by fused_plan() from the environment at plan time.  SWEEP="d,h;d,h"
 selects combinations, SWEEP=none prints only the baseline.
 """
-import itertools
 import os
 import sys
 

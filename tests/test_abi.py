@@ -1,6 +1,5 @@
 """The C-ABI library loads and exports every symbol include/pymfb.h declares (CPU only:
 no compute call is made), and the product fails loudly without a GPU."""
-import ctypes
 import os
 import re
 
