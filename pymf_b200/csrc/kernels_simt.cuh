@@ -260,14 +260,17 @@ template <int KB>
 __global__ void __launch_bounds__(SIMT_THREADS)
 k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t rows,
            const float* __restrict__ H, int64_t ldh, int64_t n_loc, int64_t cols_per_split,
-           float* __restrict__ P, int64_t ldp) {
+           float* __restrict__ P, int64_t ldp, int nrb_x, int64_t rows_h, float* __restrict__ PB) {
+    // Row blocks [0, nrb_x) of the grid compute X H^T; when PB != nullptr the remaining row blocks compute H H^T in
+    // the same launch (the streamed operand is then H itself, rows_h rows, output PB) - one launch instead of two.
     if (st->stop) return;
+    if ((int)blockIdx.x >= nrb_x) { X = H; ldx = ldh; rows = rows_h; P = PB; }
     constexpr int TK = KB / 8;
     __shared__ float Xs[128][XHT_CK + 1];
     __shared__ __align__(16) float Hs[XHT_CK][KB];
     const int tid = threadIdx.x;
     const int tr = tid & 31, tk = tid >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const int64_t row0 = (int64_t)((int)blockIdx.x >= nrb_x ? (int)blockIdx.x - nrb_x : (int)blockIdx.x) * 128;
     const int kb0 = blockIdx.z * KB;
     const int64_t c_begin = (int64_t)blockIdx.y * cols_per_split;
     const int64_t c_end = min(n_loc, c_begin + cols_per_split);

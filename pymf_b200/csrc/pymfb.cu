@@ -398,29 +398,22 @@ static int launch_xht(pymfb_ctx* c) {
     if (c->path == PYMFB_PATH_TC) {
         if (tc_xht(c->tc, c->st, Hc, c->P, c->stream, &c->launches)) return fail("tcgen05 X.H^T launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
+        // X H^T and H H^T in ONE launch: the row blocks beyond those of X stream H itself
         int64_t cps; unsigned ns;
         xht_splits(c, c->d, &cps, &ns);
-        dim3 grid((unsigned)((c->d + 127) / 128), ns, (unsigned)(c->kp / c->kb));
+        const int nrb_x = (int)((c->d + 127) / 128), nrb_h = (c->kp + 127) / 128;
+        dim3 grid((unsigned)(nrb_x + nrb_h), ns, (unsigned)(c->kp / c->kb));
+        float* PB = c->P + c->d * c->kp;
         if (c->kb == 16)
-            k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp);
+            k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
+                                                                 nrb_x, (int64_t)c->kp, PB);
         else
-            k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp);
+            k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
+                                                                 nrb_x, (int64_t)c->kp, PB);
         c->launches += 1;
         CU(cudaGetLastError());
     }
     CK(timing_end(c, 1, e0, e1));
-    if (!(c->path == PYMFB_PATH_TC && tc_xht_includes_hht(c->tc))) {   // B = H H^T  (X := H)
-        int64_t cps; unsigned ns;
-        xht_splits(c, c->kp, &cps, &ns);
-        dim3 grid((unsigned)((c->kp + 127) / 128), ns, (unsigned)(c->kp / c->kb));
-        float* PB = c->P + c->d * c->kp;
-        if (c->kb == 16)
-            k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, Hc, c->ldh, c->kp, Hc, c->ldh, c->n_loc, cps, PB, c->kp);
-        else
-            k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, Hc, c->ldh, c->kp, Hc, c->ldh, c->n_loc, cps, PB, c->kp);
-        c->launches += 1;
-        CU(cudaGetLastError());
-    }
     if (c->world > 1)
         NC(g_nccl.AllReduce(c->P, c->AB, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
     c->ab_valid = true;
