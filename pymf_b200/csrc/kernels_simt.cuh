@@ -116,9 +116,15 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
                 const float* __restrict__ W, const float* __restrict__ G,
                 const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
                 int64_t d, int64_t n_loc, int kp, float lam, const float* __restrict__ Gneg,
-                int64_t rows_per_split, float* __restrict__ Cpart, unsigned* __restrict__ tickets) {
+                int64_t rows_per_split, float* __restrict__ Cpart, unsigned* __restrict__ tickets,
+                float* __restrict__ zero_buf, int64_t zero_count) {
     // Gneg != nullptr: Semi-NMF (pymf/snmf.py:72-90) - G is then G+ and Gneg is G-
     if (st->stop) return;
+    if (zero_buf != nullptr) {   // clear the [X H^T | H H^T] partial buffer for the pass that follows (saves a k_zero launch)
+        const int64_t nb = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+        const int64_t b = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        for (int64_t i = b * blockDim.x + threadIdx.x; i < zero_count; i += nb * blockDim.x) zero_buf[i] = 0.f;
+    }
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
     __shared__ __align__(16) float Ls[2][TILE_DK][KB];

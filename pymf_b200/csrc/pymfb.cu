@@ -173,6 +173,7 @@ struct pymfb_ctx {
     double* resid_part = nullptr;
 
     bool ab_valid = false;         // AB matches the current H (and X)
+    bool p_zeroed = false;         // P was cleared by the SIMT H-update kernel and not written since
     bool g_valid = false;          // G matches the current W
     bool xx_valid = false;
 
@@ -345,14 +346,15 @@ static int launch_h_update(pymfb_ctx* c) {
             k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
                                                                       c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
-                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets);
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count);
         else
             k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
                                                                       c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
-                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets);
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count);
         c->launches += 1;
         CU(cudaGetLastError());
+        c->p_zeroed = true;            // the SIMT kernel cleared P (nothing reads [A | B] between here and the next X H^T pass)
     }
     CK(timing_end(c, 0, e0, e1));
     c->hcur ^= 1;
@@ -391,8 +393,11 @@ static void xht_splits(pymfb_ctx* c, int64_t rows, int64_t* cols_per_split, unsi
 // P = [X H^T | H H^T] for the current H, then AB = allreduce(P)
 static int launch_xht(pymfb_ctx* c) {
     const float* Hc = c->H[c->hcur];
-    k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
-    c->launches += 1;
+    if (!c->p_zeroed) {
+        k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
+        c->launches += 1;
+    }
+    c->p_zeroed = false;
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 1, &e0, &e1));
     if (c->path == PYMFB_PATH_TC) {
@@ -803,6 +808,7 @@ int pymfb_comm_destroy(void* comm) {
 
 static int data_changed(pymfb_ctx* c) {
     graph_drop(c); c->graph_key = 0;
+    c->p_zeroed = false;
     c->ab_valid = false; c->xx_valid = false;
     CK(resolve_path(c));
     if (c->path == PYMFB_PATH_TC) CK(plan_tc(c));
@@ -1201,6 +1207,7 @@ int pymfb_run(pymfb_ctx* c, int niter, unsigned flags, double* ferr_host, int* n
         if (flags & PYMFB_COMPUTE_H) c->hcur = h0 ^ (done & 1);
         CU(cudaMemsetAsync(&c->st->stop, 0, sizeof(int), c->stream));
         c->g_valid = false;   // recomputed lazily for the surviving W
+        c->p_zeroed = false;  // kernels after the stop (incl. the one that clears P) were no-ops
         c->ab_valid = false;
         c->tc.hs_valid[0] = c->tc.hs_valid[1] = false;
         if (flags & PYMFB_COMPUTE_H) {   // the penalty weights grew once per EXECUTED update_h only
