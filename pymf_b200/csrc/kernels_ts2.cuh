@@ -44,7 +44,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // relaxed: what is handed over lives in TENSOR memory and is ordered by tcgen05.wait / tcgen05.fence before this
+    // arrive; a release at cluster scope made every arrive wait ~1 us for the thread's outstanding memory traffic
+    // (first run: 2 190 cycles per stage, 7.9 ms vs 3.2 ms for the single-CTA kernel)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -60,6 +63,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         if (((++spins) & 0xFFu) == 0u) mbar_watchdog(t0);
     }
 }
+#if defined(PYMFB_TS2_WAIT_CTA)      // experiment: CTA-scope acquire on the leader's collecting barriers
+#define TS2_WAIT(bar, par) mbar_wait(bar, par)
+#else
+#define TS2_WAIT(bar, par) mbar_wait_cluster(bar, par)
+#endif
 __device__ __forceinline__ void umma2_tf32_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t bd_lo, uint32_t bd_hi, uint32_t idesc,
                                                  uint32_t accumulate) {
     asm volatile(
@@ -175,7 +183,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                     const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
                     const uint32_t b = g & 1u;
                     TRACE_AT(mc, 8);
-                    mbar_wait_cluster(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                    TS2_WAIT(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
                     bool first = true;
@@ -183,7 +191,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                         TRACE_AT(mc, 5);
                         // afull(t) implies full(s): the convert warps waited on full(s) - the barrier that also counts the
                         // [W_hi|W_lo] bytes of the stage - before they filled A slot t and arrived on afull(t)
-                        mbar_wait_cluster(afull_bar(t), tph);
+                        TS2_WAIT(afull_bar(t), tph);
                         TRACE_AT(mc, 6);
                         tc_fence_after();
                         const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;

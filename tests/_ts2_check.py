@@ -32,7 +32,7 @@ def one(d, n, k, ts2, iters):
 
 
 if __name__ == "__main__":
-    for shape in ((1024, 128 * 33, 64), (512, 128 * 8, 50)):
+    for shape in ((1024, 128 * 33, 64),):
         Ha, ta, fa = one(*shape, ts2=False, iters=3)
         Hb, tb, fb = one(*shape, ts2=True, iters=3)
         print(shape, "bit-identical:", np.array_equal(Ha, Hb), "max abs diff", float(np.max(np.abs(Ha - Hb))),
