@@ -1,4 +1,4 @@
-// kernels_ts2.cuh - CTA-pair (tcgen05 cta_group::2) variant of the TS H-update kernel, KP = 64.  EXPERIMENTAL, opt-in
+// kernels_ts2.cuh - CTA-pair (tcgen05 cta_group::2) variant of the TS H-update kernel, KP = 32 / 64.  EXPERIMENTAL, opt-in
 // with PYMFB_TS2=1: one tcgen05.mma covers M = 256 = the 128-column tiles of BOTH CTAs of a
 // cluster, so the pair issues half the instructions / commits per byte of X, and each CTA stages only 1.5 KP instead
 // of 2 KP operand columns per stage.  Derived from k_h_update_ts (kernels_tc.cuh); differences:
@@ -17,7 +17,8 @@ namespace tc {
 
 template <int KP>
 struct Ts2Cfg {
-    static constexpr int BSTAGE_BYTES = (KP / 32 + KP / 64) * R1 * 128;   // region B (KP columns) + region A (KP/2 columns)
+    static constexpr int NCHA = KP >= 64 ? KP / 64 : 1;                    // 32-column chunks of region A (KP/2 columns, padded to a chunk)
+    static constexpr int BSTAGE_BYTES = (KP / 32 + NCHA) * R1 * 128;      // region B (KP columns) + region A
     static constexpr int STAGE_BYTES = XSTAGE_BYTES + BSTAGE_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -32,7 +33,7 @@ struct Ts2Cfg {
     static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
     static constexpr int NBAR = 2 * STAGES + 2 * NT + 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
-    static_assert(KP == 64, "the CTA-pair kernel serves KP = 64 (region A must be whole 32-column chunks)");
+    static_assert(KP == 32 || KP == 64, "the CTA-pair kernel serves KP = 32 and 64");
     static_assert(NBAR * 8 + 8 <= 512, "barrier area too small");
     static_assert(SMEM_BYTES <= SMEM_LIMIT, "stage ring does not fit");
 };
@@ -157,7 +158,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
                         for (int c = 0; c < KP / 32; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), (int)rank * KP + 32 * c, r0);
 #pragma unroll
-                        for (int c = 0; c < KP / 64; ++c) tma_load_2d(wch(s) + (KP / 32 + c) * (R1 * 128), mb, full_bar(s), (int)rank * (KP / 2) + 32 * c, r0);
+                        for (int c = 0; c < Cfg::NCHA; ++c) tma_load_2d(wch(s) + (KP / 32 + c) * (R1 * 128), mb, full_bar(s), (int)rank * (KP / 2) + 32 * c, r0);
                     }
                     __syncwarp();
                     }
@@ -349,12 +350,13 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 // ---- host side: opt-in with PYMFB_TS2=1 on shapes the TS kernels serve with kp = 64 ----
 inline bool ts2_wanted(const TcPlan& p) {
     const char* e = getenv("PYMFB_TS2");
-    return e && e[0] == '1' && p.ready && p.use_ts && p.kp == 64 && p.sm_count >= 2;
+    return e && e[0] == '1' && p.ready && p.use_ts && (p.kp == 64 || p.kp == 32) && p.sm_count >= 2;
 }
 inline int ts2_prepare(TcPlan& p) {
     p.use_ts2 = false;
     if (!ts2_wanted(p)) return 0;
-    if (cudaFuncSetAttribute(tc::k_h_update_ts2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Ts2Cfg<64>::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc::k_h_update_ts2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Ts2Cfg<64>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::k_h_update_ts2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Ts2Cfg<32>::SMEM_BYTES) != cudaSuccess)
         return 1;
     p.use_ts2 = true;
     return 0;
@@ -365,9 +367,14 @@ inline int ts2_h_update(TcPlan& p, const DevState* st, const float* Hc, float* H
     p.hs_valid[hsrc ^ 1] = true;
     const int nsuper = (p.h_tiles + 1) / 2;
     const int grid = 2 * std::min(nsuper, p.sm_count / 2);
-    tc::k_h_update_ts2<64><<<grid, tc::Ts2Cfg<64>::THREADS, tc::Ts2Cfg<64>::SMEM_BYTES, stream>>>(
-        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
-        p.lam_h, p.Dp, p.Dn);
+    if (p.kp == 64)
+        tc::k_h_update_ts2<64><<<grid, tc::Ts2Cfg<64>::THREADS, tc::Ts2Cfg<64>::SMEM_BYTES, stream>>>(
+            p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
+            p.lam_h, p.Dp, p.Dn);
+    else
+        tc::k_h_update_ts2<32><<<grid, tc::Ts2Cfg<32>::THREADS, tc::Ts2Cfg<32>::SMEM_BYTES, stream>>>(
+            p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
+            p.lam_h, p.Dp, p.Dn);
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
