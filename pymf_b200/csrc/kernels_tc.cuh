@@ -1461,9 +1461,14 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
             p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr);
     }
 }
+// experiment knob: PYMFB_GRID caps the CTA count of the H-update kernels (per-SM pipeline capacity measurements)
+inline int grid_cap(int grid) {
+    static const int cap = [] { const char* e = getenv("PYMFB_GRID"); return e ? atoi(e) : 0; }();
+    return cap > 0 ? std::min(grid, cap) : grid;
+}
 template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
-    const int grid = std::min(p.h_tiles, p.sm_count);
+    const int grid = grid_cap(std::min(p.h_tiles, p.sm_count));
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.lam_h, p.Dp, p.Dn);
 }

@@ -366,7 +366,7 @@ inline int ts2_h_update(TcPlan& p, const DevState* st, const float* Hc, float* H
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
     p.hs_valid[hsrc ^ 1] = true;
     const int nsuper = (p.h_tiles + 1) / 2;
-    const int grid = 2 * std::min(nsuper, p.sm_count / 2);
+    const int grid = 2 * std::min(nsuper, grid_cap(p.sm_count) / 2);
     if (p.kp == 64)
         tc::k_h_update_ts2<64><<<grid, tc::Ts2Cfg<64>::THREADS, tc::Ts2Cfg<64>::SMEM_BYTES, stream>>>(
             p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
