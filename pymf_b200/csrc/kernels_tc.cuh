@@ -679,8 +679,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 #ifndef PYMFB_NCHAIN
 #define PYMFB_NCHAIN 1   // 2 was measured: no change (316 vs 309 us on the per-SM-bound probe), so the default stays 1
 #endif
+#ifndef PYMFB_H_CONV_GROUPS
+#define PYMFB_H_CONV_GROUPS 1   // convert-warp groups of the TS H-update kernel (2 = alternate stages, 16 warps per CTA)
+#endif
 template <int KP>
 struct TsCfg {
+    static constexpr int CONV_GROUPS = PYMFB_H_CONV_GROUPS;
     static constexpr int NCH = 2 * KP / 32;
     static constexpr int BSTAGE_BYTES = NCH * R1 * 128;             // [b_hi | b_lo] operand per stage (= 2*KP*128)
     static constexpr int STAGE_BYTES = XSTAGE_BYTES + BSTAGE_BYTES;
@@ -698,7 +702,7 @@ struct TsCfg {
     static constexpr int NT = NT_RAW > 6 ? 6 : NT_RAW;
     static constexpr int EPI_WARPS = 4;
     static constexpr int NJ = KP;
-    static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
+    static constexpr int THREADS = 32 * (NPROD + 1 + 4 * CONV_GROUPS + EPI_WARPS);
     static constexpr int NBAR = 2 * STAGES + 2 * NT + 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
     static_assert(KP == 32 || KP == 64, "TS kernels serve KP = 32 and 64");
@@ -861,14 +865,22 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp < NPROD + 5) {
+    } else if (warp < NPROD + 1 + 4 * Cfg::CONV_GROUPS) {
         // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
+        // CONV_GROUPS groups of 4 warps take alternate stages (every waiter still sees consecutive phases of the
+        // barriers it waits on: a slot's next use needs this group's own arrival first)
         const int q = warp & 3;
+        const int group = (warp - (NPROD + 1)) >> 2;
         const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
         int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int it = 0; it < nit; ++it, ++cc) {
+                if (Cfg::CONV_GROUPS > 1 && (int)(cc % Cfg::CONV_GROUPS) != group) {
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                    continue;
+                }
                 if (q == 0) TRACE_AT(cc, 2);
                 mbar_wait(full_bar(s), ph);
                 if (q == 0) TRACE_AT(cc, 9);
