@@ -433,3 +433,27 @@ def test_c_abi_reports_errors_instead_of_crashing():
         assert e.run(0)[1] == 0                    # niter = 0 is a no-op
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("shape", [(1024, 128 * 33, 64), (700, 128 * 9 + 5, 20)])
+def test_cta_pair_h_update_kernel_is_bit_identical(shape, monkeypatch):
+    """Opt-in CTA-pair (tcgen05 cta_group::2) H-update kernel (PYMFB_TS2=1, kernels_ts2.cuh): same MMAs in the same
+    order as the single-CTA kernel, so one H update must be bit-identical - odd tile count (virtual OOB tile), ragged n."""
+    d, n, k = shape
+    out = []
+    for ts2 in (False, True):
+        if ts2:
+            monkeypatch.setenv("PYMFB_TS2", "1")
+        else:
+            monkeypatch.delenv("PYMFB_TS2", raising=False)
+        e = pymf_b200.Engine(d, n, k, path="tc")
+        try:
+            e.gen_x(1); e.gen_w(2); e.gen_h(3)
+            e.run(1, compute_w=False, compute_h=True, compute_err=False, early_stop=False)
+            H = e.get_h(np.float32)
+            f, _ = e.run(2, early_stop=False)
+            out.append((H, f))
+        finally:
+            e.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
