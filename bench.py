@@ -1,25 +1,55 @@
 #!/usr/bin/env python
 """bench.py - NMF multiplicative-update iterations/s on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
 
 A "step" is one NMF iteration (W update, H update, Frobenius error; compute_w = compute_h =
-compute_err = True) over the whole synthetic matrix.  Workload (default): BASELINE.json
-configs[1], 4096 x 262144 fp32, k = 32 PER GPU; with N GPUs the matrix is N x 262144 columns
-(column shards, weak scaling) and `value` counts shard-iterations/s summed over ranks, so at
-N = 1 it is plain iterations/s.
+compute_err = True) over the whole synthetic matrix.
 
-Prints ONE JSON line (rank 0).  `value`: X resident in HBM, device-timed with CUDA events, max
-over ranks.  `e2e`: the same metric through pymf_b200.NMF with HOST buffers (upload of X/W/H,
-K iterations, download of W/H/ferr all inside the timed region).  `roofline`: the streaming
-kernels' algorithmic bytes / their CUDA-event time vs MEASURED_PEAKS.json.  `cpu_baseline`: the
-numpy oracle port of the reference path timed on this box's host cores on a column prefix.
---impl reference: only the CPU arm (the reference is pure Python/numpy; the oracle port is it).
+Default workload = BASELINE.json configs[2], the north-star target: 16384 x 1048576 fp32, k = 128
+(64 GiB, fits one B200), STRONG scaling - with N GPUs every rank owns n/N columns and `value` is
+iterations/s of the one global problem.  `secondary` in the same line is configs[1] (4096 x 262144,
+k = 32, the memory-bound regime) with its own value and roofline, 262144 columns PER GPU (weak).
+The other workloads (--workload cfg2, cfg4k*, cfg5, cfg1) are weak-scaled per-GPU shards.
+
+Prints ONE JSON line (rank 0):
+  value         X resident in HBM, device-timed with CUDA events on the library's stream, max over ranks
+  roofline      the streaming kernels against the roof that binds them (3xTF32 tensor work vs half the
+                measured bf16 rate, or algorithmic bytes vs the measured copy bandwidth; both fractions given)
+  e2e           the same metric through the public class API, pymf_b200.NMF(X_host).factorize(K), with
+                page-locked HOST buffers: upload of X/W/H, K iterations, download of W/H/ferr all timed
+  e2e_pageable  the same from ordinary (pageable) numpy arrays - what a drop-in pymf.NMF(numpy_array) caller sees
+  cpu_baseline  the reference's own pymf/nmf.py (loaded unmodified by path) on this box's host cores, on a
+                column prefix of the workload, measured rate and the rate extrapolated to the full n
+  parity_vs_golden  a small fixed problem run on the same N ranks and compared with tests/golden (reference output)
+--impl reference: only the CPU arm (rank 0), same config / metric / unit.
 """
-import argparse
-import json
 import os
 import sys
+
+
+def _host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def _impl_from_argv(argv):
+    for i, a in enumerate(argv):
+        if a == "--impl" and i + 1 < len(argv):
+            return argv[i + 1]
+        if a.startswith("--impl="):
+            return a.split("=", 1)[1]
+    return "ours"
+
+
+# torch.distributed.run exports OMP_NUM_THREADS=1 when nproc > 1, which would make the reference arm's BLAS
+# single-threaded: the CPU arm always gets every core of the affinity mask (set before numpy loads OpenBLAS,
+# and again through threadpoolctl at run time; the count actually used is printed in cpu_baseline).
+if _impl_from_argv(sys.argv) == "reference":
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_cores())
+
+import argparse
+import json
 import threading
 import time
 
@@ -30,17 +60,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (d, n per GPU, k, description)
-    "cfg1": (1000, 500, 10, "cfg1: 1000x500, k=10"),
-    "cfg2": (4096, 262144, 32, "cfg2: 4096x262144 fp32, k=32"),
-    "cfg3": (16384, 1048576, 128, "cfg3: 16384x1M fp32, k=128 (STRONG: columns split over GPUs)"),
-    "cfg4k64": (8192, 524288, 64, "cfg4: 8192x524288, k=64"),
-    "cfg4k16": (8192, 524288, 16, "cfg4: 8192x524288, k=16"),
-    "cfg4k32": (8192, 524288, 32, "cfg4: 8192x524288, k=32"),
-    "cfg4k128": (8192, 524288, 128, "cfg4: 8192x524288, k=128"),
-    "cfg4k256": (8192, 524288, 256, "cfg4: 8192x524288, k=256"),
-    "cfg4k512": (8192, 524288, 512, "cfg4: 8192x524288, k=512"),
-    "cfg5": (32768, 524288, 64, "cfg5: 32768x524288 per GPU (64 GiB), k=64, weak scaling"),
+    # name: (d, n [per GPU if weak, global if strong], k, scaling, description)
+    "cfg1": (1000, 500, 10, "weak", "cfg1: 1000x500, k=10"),
+    "cfg2": (4096, 262144, 32, "weak", "cfg2: 4096x262144 fp32, k=32"),
+    "cfg3": (16384, 1048576, 128, "strong", "cfg3: 16384x1M fp32, k=128, columns split over the GPUs"),
+    "cfg4k64": (8192, 524288, 64, "weak", "cfg4: 8192x524288, k=64"),
+    "cfg4k16": (8192, 524288, 16, "weak", "cfg4: 8192x524288, k=16"),
+    "cfg4k32": (8192, 524288, 32, "weak", "cfg4: 8192x524288, k=32"),
+    "cfg4k128": (8192, 524288, 128, "weak", "cfg4: 8192x524288, k=128"),
+    "cfg4k256": (8192, 524288, 256, "weak", "cfg4: 8192x524288, k=256"),
+    "cfg4k512": (8192, 524288, 512, "weak", "cfg4: 8192x524288, k=512"),
+    "cfg5": (32768, 524288, 64, "weak", "cfg5: 32768x524288 per GPU (64 GiB), k=64, weak scaling"),
 }
 # --mode: which of factorize()'s flag combinations a step is (tests/test_pymf.py:92-95 of the reference)
 MODES = {
@@ -50,6 +80,8 @@ MODES = {
 }
 METRIC = "NMF MU iterations/sec"
 UNIT = "iterations/s"
+PARITY_CASE = "scale_k128"       # tests/golden/traj_scale_k128.npz: 1024 x 2048, k = 128, 6 iterations (oracle/cases.py)
+PARITY_SEED, PARITY_SHAPE, PARITY_NITER = 801, (1024, 2048, 128), 6
 
 
 def measured_peaks():
@@ -118,118 +150,207 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_port_rate(d, n_full, k, budget_s, steps, warmup):
-    """Time the numpy oracle port (same arithmetic as pymf/nmf.py) on a column prefix of the
-    workload and extrapolate to n_full (time is linear in n).  Returns (it/s at n_full,
-    sample description, cores, measured seconds/iteration on the prefix, n_cpu)."""
+def _blas_threads(cores):
+    """Force the BLAS pool to `cores` threads whatever the launcher exported; returns the count in effect."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+        info = threadpoolctl.threadpool_info()
+        blas = [i.get("num_threads") for i in info if i.get("user_api") == "blas"]
+        return int(max(blas)) if blas else None
+    except Exception:
+        return None
+
+
+def cpu_arm(d, n_full, k, budget_s, steps, warmup):
+    """Time the reference's NMF loop (pymf/nmf.py:141-202, the UNMODIFIED file loaded by path through
+    oracle/ref_loader.py; the numpy oracle port only if no copy of the reference is on this box) on a
+    float64 column prefix of the workload with the same d and k.  The host cannot hold the full matrix
+    plus the reference's three d x n float64 temporaries, and its time is linear in n, so the full-size
+    rate is the measured prefix rate scaled by n_cpu / n_full - both are returned."""
     from oracle import nmf_oracle as O
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    from oracle.ref_loader import find_reference, load_reference_nmf
+    cores = _host_cores()
+    blas = _blas_threads(cores)
+    ref = load_reference_nmf()
+    kind = "reference" if ref is not None else "port"
     rng = np.random.RandomState(0)
 
-    def one(n_cpu, iters):
+    def iterate(X, W, H, iters):
+        if ref is not None:
+            m = ref.NMF(X, num_bases=k)
+            m.W, m.H = W, H
+            for _ in range(iters):
+                m.factorize(niter=1)          # niter=1 never reaches the i > 1 convergence test (pymf/nmf.py:198)
+        else:
+            O.factorize(X, W, H, niter=iters, early_stop=False)
+
+    def timed(n_cpu, iters, warm):
         X = rng.random_sample((d, n_cpu))
         W = rng.random_sample((d, k))
         H = rng.random_sample((k, n_cpu))
-        O.factorize(X, W, H, niter=1, early_stop=False)          # warm BLAS threads
+        iterate(X, W, H, warm)
         t0 = time.perf_counter()
-        O.factorize(X, W, H, niter=iters, early_stop=False)
+        iterate(X, W, H, iters)
         return (time.perf_counter() - t0) / iters
 
-    n_probe = min(n_full, 2048)
-    t_probe = one(n_probe, 2)
+    n_probe = min(n_full, 1024)
+    t_probe = timed(n_probe, 1, 1)
     total_iters = max(1, steps + warmup)
-    # largest power-of-two prefix such that all iterations fit the budget (and RAM: 5 d*n f64 temps)
+    # largest power-of-two prefix whose iterations fit the time budget and RAM (5 d x n float64 temporaries)
     n_cpu = n_probe
     while (n_cpu * 2 <= n_full and t_probe * (n_cpu * 2 / n_probe) * total_iters <= budget_s
            and 5 * 8 * d * n_cpu * 2 <= 8e9):
         n_cpu *= 2
-    X = rng.random_sample((d, n_cpu))
-    W = rng.random_sample((d, k))
-    H = rng.random_sample((k, n_cpu))
-    O.factorize(X, W, H, niter=max(1, warmup), early_stop=False)
-    t0 = time.perf_counter()
-    O.factorize(X, W, H, niter=steps, early_stop=False)
-    sec = (time.perf_counter() - t0) / steps
+    sec = timed(n_cpu, steps, max(1, warmup))
+    rate_prefix = 1.0 / sec
     rate_full = 1.0 / (sec * (float(n_full) / n_cpu))
-    sample = ("numpy float64 port of pymf/nmf.py update_w/update_h/frobenius_norm, %d iterations on a "
-              "%dx%d column prefix (k=%d), %.3f s/iter measured, extrapolated linearly in n to %d columns"
-              % (steps, d, n_cpu, k, sec, n_full))
-    return rate_full, sample, cores, sec, n_cpu
+    what = ("unmodified pymf/nmf.py NMF.factorize (%s)" % find_reference()) if ref is not None else \
+        "numpy float64 port of pymf/nmf.py (oracle/nmf_oracle.py; no copy of the reference on this box)"
+    if n_cpu != n_full:
+        sample = ("%s, float64, %d iterations on a %dx%d column prefix (k=%d): %.3f s/iter measured = %.4g it/s on the "
+                  "prefix; `value` is that rate scaled linearly in n to %d columns (extrapolated)"
+                  % (what, steps, d, n_cpu, k, sec, rate_prefix, n_full))
+    else:
+        sample = "%s, float64, %d iterations on the full %dx%d matrix (k=%d): %.4f s/iter" % (what, steps, d, n_cpu, k, sec)
+    return {"value": rate_full, "unit": UNIT, "cores": cores, "blas_threads": blas, "kind": kind, "sample": sample,
+            "measured_prefix_value": rate_prefix, "prefix_columns": n_cpu, "full_columns": n_full,
+            "seconds_per_iteration_on_prefix": sec, "extrapolated": n_cpu != n_full,
+            "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")}
 
 
-def run_reference(args, d, n_per_gpu, k, wl_desc):
+def run_reference(args, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    d, n, k, scaling, desc = WORKLOADS[wl_name]
     steps = max(1, args.steps)
-    rate, sample, cores, sec, n_cpu = cpu_port_rate(d, n_per_gpu, k, budget_s=150.0, steps=steps,
-                                                    warmup=max(1, args.warmup))
+    n_full = n if scaling == "strong" else n          # weak: one shard (the host does every shard in turn)
+    cpu = cpu_arm(d, n_full, k, budget_s=150.0, steps=steps, warmup=max(1, args.warmup))
+    rate = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_desc, "d": d, "n_per_gpu": n_per_gpu, "k": k,
-                   "note": "CPU arm: one host does every shard, so shard-iterations/s does not grow with N"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "d": d, "n_global" if scaling == "strong" else "n_per_gpu": n, "k": k,
+                   "note": "CPU arm: one host runs the reference's loop; its rate does not depend on N"},
+        "cpu_baseline": cpu,
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- GPU arm
-def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
-    import torch
-    import torch.distributed as dist
-    import pymf_b200
+class Dist(object):
+    """Rank plumbing shared by the legs (torch.distributed over NCCL when world > 1)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            sys.exit("--gpus %d needs torchrun (WORLD_SIZE=%d)" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            sys.exit("--gpus %d needs torchrun (WORLD_SIZE=%d)" % (args.gpus, self.world))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
 
-    strong = wl_name == "cfg3"
-    if strong:
-        n_global = n_per_gpu
-        bounds = [(n_global * r) // world for r in range(world + 1)]
-        n_loc, col0 = bounds[rank + 1] - bounds[rank], bounds[rank]
-    else:
-        n_global, n_loc, col0 = n_per_gpu * world, n_per_gpu, n_per_gpu * rank
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def reduce(self, x, op="max"):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return float(t.item())
 
-    eng = pymf_b200.Engine(d, n_loc, k, device=local_rank, n_global=n_global, col0=col0,
-                           path=args.path)
-    if world > 1:
-        box = [pymf_b200.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        eng.comm_init(box[0], world, rank)
+    def attach(self, pymf_b200, eng):
+        if self.dist is None:
+            return
+        box = [pymf_b200.Engine.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], self.world, self.rank)
+
+    def shard(self, n, scaling):
+        """(n_global, n_local, first column) of this rank's block."""
+        if scaling == "strong":
+            b = [(n * r) // self.world for r in range(self.world + 1)]
+            return n, b[self.rank + 1] - b[self.rank], b[self.rank]
+        return n * self.world, n, n * self.rank
+
+
+def roofline_of(d, n_loc, k, mode, t_h, t_x, n_timed, ms_per_step, small, wl_name, world, path):
+    """bytes_alg = 4 d n_loc + 8 k n_loc, flops_alg = 4 d n_loc k + 4 n_loc k^2 + 4 d k^2 per
+    iteration per GPU; the tensor pipe executes 3 x flops_alg (3xTF32 split) at the TF32 dense rate, taken as
+    HALF the measured bf16 rate (tests/mma_probe.cu: a kind::tf32 MMA of K = 8 costs the cycles of a kind::f16
+    MMA of K = 16).  The bound is whichever roof gives the longer minimum time."""
+    hbm_peak, bf16_peak, peak_kind = measured_peaks()
+    tf32_peak = 0.5 * bf16_peak
+    bytes_alg = 4.0 * d * n_loc + 8.0 * k * n_loc
+    flops_alg = 4.0 * d * n_loc * k + 4.0 * n_loc * k * k + 4.0 * d * k * k
+    if mode == "w_only":
+        bytes_alg = 0.0
+    if mode == "h_only":
+        flops_alg = 2.0 * d * n_loc * k + 2.0 * n_loc * k * k
+    t_stream_ms = ms_per_step if small else (t_h + t_x)
+    t_s = t_stream_ms * 1e-3
+    gbs = bytes_alg / t_s / 1e9 if t_s > 0 else 0.0
+    tf = 3.0 * flops_alg / t_s / 1e12 if t_s > 0 else 0.0
+    hbm_frac, tensor_frac = gbs / hbm_peak, tf / tf32_peak
+    t_min_hbm, t_min_tensor = bytes_alg / (hbm_peak * 1e9), 3.0 * flops_alg / (tf32_peak * 1e12)
+    tensor_bound = t_min_tensor > t_min_hbm
+    traffic = None
+    try:                       # DRAM bytes per iteration of the streaming kernels, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl_name)
+        if tj and world == 1 and path == "tc":
+            traffic = tj["h_update_bytes"] + tj["xht_bytes"]
+    except Exception:
+        traffic = None
+    r = {
+        "bound": "tensor" if tensor_bound else "hbm",
+        "achieved": tf if tensor_bound else gbs,
+        "peak": tf32_peak if tensor_bound else hbm_peak,
+        "unit": "TFLOP/s" if tensor_bound else "GB/s",
+        "frac": tensor_frac if tensor_bound else hbm_frac,
+        "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of the same kernels)",
+        "peak_kind": peak_kind,
+        "peak_note": ("TF32 dense peak = bf16_tflops_sustained / 2 from MEASURED_PEAKS.json; achieved = 3 x flops_alg "
+                      "(3xTF32 split) / kernel time") if tensor_bound else "hbm_gbs from MEASURED_PEAKS.json (copy bandwidth)",
+        "kernel": "streaming kernels of one iteration (H-update pass + X.H^T pass, or the one-pass kernel), CUDA events "
+                  "on the launch stream, per-launch average",
+        "alg_bytes_per_iteration": bytes_alg, "alg_flops_per_iteration": flops_alg,
+        "h_update_ms": t_h, "xht_ms": t_x, "kernel_launches_timed": int(n_timed),
+        "hbm_frac": hbm_frac, "tensor_frac": tensor_frac,
+        "min_ms_hbm": t_min_hbm * 1e3, "min_ms_tensor": t_min_tensor * 1e3,
+        "fp32_equiv_tflops": flops_alg / t_s / 1e12 if t_s > 0 else 0.0,
+        "share_of_step": (t_stream_ms / ms_per_step) if ms_per_step > 0 else None,
+    }
+    return r
+
+
+def device_leg(D, pymf_b200, args, wl_name, steps, warmup, mode):
+    """X generated on the device and resident; W steps untimed, then K steps between CUDA events."""
+    d, n, k, scaling, desc = WORKLOADS[wl_name]
+    n_global, n_loc, col0 = D.shard(n, scaling)
+    eng = pymf_b200.Engine(d, n_loc, k, device=D.local_rank, n_global=n_global, col0=col0, path=args.path)
+    D.attach(pymf_b200, eng)
     eng.gen_x(1234)
     eng.gen_w(1235)
     eng.gen_h(1236)
     eng.sync()
-
-    steps, warmup = max(1, args.steps), max(3, args.warmup)
-    mode_kw = MODES[args.mode]
+    mode_kw = MODES[mode]
     eng.enqueue(warmup, **mode_kw)
     eng.sync()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    D.barrier()
+    sampler = ClockSampler(D.local_rank) if D.rank == 0 else None
     if sampler:
         sampler.start()
     # per-kernel CUDA events only on streaming-sized problems: small ones are launch-bound and replay the
@@ -238,14 +359,14 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     eng.kernel_timing(not small)
     l0, g0 = eng.launch_count, eng.graph_replays
     e0, e1 = eng.event(), eng.event()
-    barrier()
+    D.barrier()
     eng.record(e0)
     eng.enqueue(steps, **mode_kw)
     eng.record(e1)
     eng.sync()
-    barrier()
-    ms = max_over_ranks(eng.elapsed_ms(e0, e1))
-    launches = (eng.launch_count - l0) * world
+    D.barrier()
+    ms = D.reduce(eng.elapsed_ms(e0, e1), "max")
+    launches = (eng.launch_count - l0) * D.world
     graph_replays = eng.graph_replays - g0
     clocks = sampler.finish() if sampler else None
     t_h, n_h = eng.kernel_timing_read(0)
@@ -253,123 +374,166 @@ def run_ours(args, d, n_per_gpu, k, wl_name, wl_desc):
     eng.kernel_timing(False)
     ferr_check = eng.frobenius()
     path = eng.active_path
-
-    ms_per_step = ms / steps
-    units_per_step = 1.0 if strong else float(world)          # shard-iterations per step
-    value = units_per_step * 1000.0 / ms_per_step
-
-    # ---- roofline of the streaming pass: bytes_alg = 4 d n_loc + 8 k n_loc per iteration
-    hbm_peak, bf16_peak, peak_kind = measured_peaks()
-    bytes_alg = 4.0 * d * n_loc + 8.0 * k * n_loc
-    if args.mode == "w_only":
-        bytes_alg = 0.0                            # no streaming pass at all
-    flops_alg = 4.0 * d * n_loc * k + 4.0 * n_loc * k * k + 4.0 * d * k * k
-    if args.mode == "h_only":
-        flops_alg = 2.0 * d * n_loc * k + 2.0 * n_loc * k * k      # W^T X and G H only
-    t_stream_ms = t_h + t_x
-    if small:                                     # no per-kernel events: the whole iteration is the unit
-        t_stream_ms = ms_per_step
-    achieved = bytes_alg / (t_stream_ms * 1e-3) / 1e9 if t_stream_ms > 0 else 0.0
-    traffic = None
-    try:                                          # DRAM bytes per iteration of the two streaming kernels (ncu capture)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl_name)
-        if tj and world == 1 and path == "tc":
-            traffic = tj["h_update_bytes"] + tj["xht_bytes"]
-    except Exception:
-        traffic = None
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-        "kernel": "streaming pass = H-update kernel + X.H^T kernel (each reads X once per iteration)",
-        "alg_bytes_per_iteration": bytes_alg, "h_update_ms": t_h, "xht_ms": t_x,
-        "kernel_launches_timed": int(n_h + n_x),
-        # each streaming kernel on its own: its bytes (X once + H read/write resp. X once + [H_hi;H_lo]) / its time
-        "h_update_frac_of_peak": (bytes_alg / (t_h * 1e-3) / 1e9 / hbm_peak) if t_h > 0 else None,
-        "xht_frac_of_peak": (bytes_alg / (t_x * 1e-3) / 1e9 / hbm_peak) if t_x > 0 else None,
-        "fp32_equiv_tflops": flops_alg / (t_stream_ms * 1e-3) / 1e12 if t_stream_ms > 0 else 0.0,
-        "tensor_frac_3xtf32_of_half_bf16_peak": (3.0 * flops_alg / (t_stream_ms * 1e-3) / 1e12) / (0.5 * bf16_peak)
-        if t_stream_ms > 0 else 0.0,
-    }
     eng.close()
+    ms_per_step = ms / steps
+    units = 1.0 if scaling == "strong" else float(D.world)
+    x_bytes = 4.0 * d * n_loc
+    return {
+        "value": units * 1000.0 / ms_per_step, "ms_per_step": ms_per_step, "scaling": scaling,
+        "launches": int(launches), "graph_replays": int(graph_replays), "clocks": clocks,
+        "roofline": roofline_of(d, n_loc, k, mode, t_h, t_x, n_h + n_x, ms_per_step, small, wl_name, D.world, path),
+        "config": {"workload": desc + (" per GPU, n_global = %d" % n_global if scaling == "weak" else
+                                       " (STRONG scaling: n_local = n / N)"),
+                   "mode": mode, "d": d, "n_local": n_loc, "n_global": n_global, "k": k, "kernel_path": path,
+                   "arithmetic": "fp32 storage; 3xTF32 tcgen05 products (tc path) or fp32 FMA (simt path); fp64 error combine",
+                   "l2": ("inputs larger than L2 (X shard = %.2f GiB), no flush needed" % (x_bytes / 2 ** 30))
+                   if x_bytes > 2 * 126e6 else
+                   ("X shard = %.1f MB fits the 126 MB L2 and is NOT flushed between iterations: the loop re-reads "
+                    "the same matrix every step by construction (latency-bound workload, no HBM roofline claim)"
+                    % (x_bytes / 1e6)),
+                   "value_units": "iterations/s of the global problem" if scaling == "strong"
+                   else "shard-iterations/s summed over ranks",
+                   "allreduce_bytes_per_step": (d * k + k * k) * 4 if D.world > 1 else 0,
+                   "ferr_after": ferr_check},
+    }
 
-    # ---- e2e: pymf_b200.NMF with host buffers (upload + K iterations + download in the timed region)
-    e2e = None
+
+def _fill_from_device(torch, host, seed):
+    """Fill a (d x n) float32 host array with U[0,1) values generated on the GPU (numpy's generator would
+    need a minute for 64 GiB); setup only, outside every timed region."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    d, n = host.shape
+    rows = max(1, min(d, (512 << 20) // (4 * n)))
+    t = torch.from_numpy(host)
+    for r0 in range(0, d, rows):
+        r1 = min(d, r0 + rows)
+        t[r0:r1].copy_(torch.rand((r1 - r0, n), device="cuda", dtype=torch.float32, generator=g))
+    torch.cuda.synchronize()
+
+
+def e2e_leg(D, pymf_b200, args, wl_name, steps, source):
+    """The drop-in user's call sequence on HOST arrays, public API only, everything inside the timed region:
+       m = NMF(X, num_bases=k); m.W = W0; m.H = H0; m.factorize(niter=K); m.W; m.H; m.ferr"""
+    torch = D.torch
+    d, n, k, scaling, desc = WORKLOADS[wl_name]
+    n_global, n_loc, col0 = D.shard(n, scaling)
+    rng = np.random.default_rng(1234 + D.rank)
+    if source == "pinned":                   # page-locked host buffers: the copy engines read them directly
+        Xh = pymf_b200.pinned_empty((d, n_loc), np.float32)
+        W0 = pymf_b200.pinned_empty((d, k), np.float64)
+        H0 = pymf_b200.pinned_empty((k, n_loc), np.float64)
+    else:                                    # ordinary pageable numpy arrays
+        Xh = np.empty((d, n_loc), np.float32)
+        W0 = np.empty((d, k), np.float64)
+        H0 = np.empty((k, n_loc), np.float64)
+    _fill_from_device(torch, Xh, 99 + D.rank)
+    # Two passes of the identical user-level sequence; the second is the one reported.  The first pays this
+    # process's one-off costs for a matrix of this size (first device allocation of the shard and its DMA
+    # mapping) and is reported beside it as `first_call_seconds`.
+    rec = []
+    for _pass in range(2):
+        rng.random(out=W0)
+        rng.random(out=H0)
+        D.barrier()
+        t0 = time.perf_counter()
+        m = pymf_b200.NMF(Xh, num_bases=k, device=D.local_rank, path=args.path,
+                          process_group=(True if D.world > 1 else None))
+        m.W, m.H = W0, H0
+        m.factorize(niter=steps)
+        res = (m.W, m.H, m.ferr)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        assert res[0] is W0 and res[1] is H0 and len(res[2]) == steps and np.isfinite(res[2]).all()
+        rec.append((D.reduce(t1 - t0, "max"), dict(m.timings), bool(m._engine.last_upload_pinned)))
+        del m, res
+    t_e2e, timings, direct = rec[1]
+    units = 1.0 if scaling == "strong" else float(D.world)
+    h2d = (Xh.nbytes + W0.nbytes + H0.nbytes) / float(steps)
+    d2h = (W0.nbytes + H0.nbytes + 8 * steps) / float(steps)
+    del Xh, W0, H0
+    return {"value": units * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "seconds_total": t_e2e, "seconds_upload": timings.get("upload_s"),
+            "seconds_iterations": timings.get("iterate_s"), "first_call_seconds": rec[0][0],
+            "host_source": source, "x_upload_direct_dma": direct, "workload": wl_name,
+            "what": "m = NMF(X_host, num_bases=k); m.W = W0; m.H = H0; m.factorize(niter=%d); m.W; m.H; m.ferr - "
+                    "construction, X/W/H upload, iterations and W/H/ferr download all timed; second of two "
+                    "identical calls in this process" % steps}
+
+
+def parity_leg(D, pymf_b200):
+    """Cross-rank parity inside the bench line: the fixed `scale_k128` problem (device generator, seeds 801-803)
+    column-sharded over the same N ranks, against the reference's output committed in tests/golden."""
+    path = os.path.join(ROOT, "tests", "golden", "traj_%s.npz" % PARITY_CASE)
+    if not os.path.isfile(path):
+        return {"case": PARITY_CASE, "unavailable": "golden fixture missing"}
+    g = np.load(path)
+    d, n, k = PARITY_SHAPE
+    n_global, n_loc, col0 = D.shard(n, "strong")
+    eng = pymf_b200.Engine(d, n_loc, k, device=D.local_rank, n_global=n_global, col0=col0)
+    D.attach(pymf_b200, eng)
+    eng.gen_x(PARITY_SEED)
+    eng.gen_w(PARITY_SEED + 1)
+    eng.gen_h(PARITY_SEED + 2)
+    ferr, done = eng.run(PARITY_NITER, early_stop=False)
+    W, H = eng.get_w(), eng.get_h()
+    path_used = eng.active_path
+    eng.close()
+    Wg = g["W_%d" % PARITY_NITER].astype(np.float64)
+    Hg = g["H_%d" % PARITY_NITER].astype(np.float64)[:, col0:col0 + n_loc]
+    rel_w = float(np.linalg.norm(W - Wg) / np.linalg.norm(Wg))
+    num = D.reduce(float(np.sum((H - Hg) ** 2)), "sum")
+    den = D.reduce(float(np.sum(Hg ** 2)), "sum")
+    rel_w = D.reduce(rel_w, "max")                     # W is replicated: worst rank
+    rel_f = float(np.max(np.abs(ferr - g["ferr"]) / g["ferr"]))
+    rel_h = float(np.sqrt(num / den))
+    return {"case": "%s %dx%d k=%d, %d iterations, %d column shard(s)" % (PARITY_CASE, d, n, k, PARITY_NITER, D.world),
+            "against": "tests/golden/traj_%s.npz (unmodified reference, float64)" % PARITY_CASE,
+            "rel_w": rel_w, "rel_h": rel_h, "rel_ferr": rel_f, "tol_wh": 1e-4, "tol_ferr": 1e-3,
+            "kernel_path": path_used, "ok": bool(rel_w < 1e-4 and rel_h < 1e-4 and rel_f < 1e-3)}
+
+
+def run_ours(args, wl_name):
+    import pymf_b200
+    D = Dist(args)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    d, n, k, scaling, desc = WORKLOADS[wl_name]
+
+    main = device_leg(D, pymf_b200, args, wl_name, steps, warmup, args.mode)
+    secondary = None
+    if wl_name == "cfg3" and args.mode == "full" and not args.no_secondary:
+        s = device_leg(D, pymf_b200, args, "cfg2", steps, warmup, "full")
+        secondary = {"metric": METRIC, "value": s["value"], "unit": UNIT, "ms_per_step": s["ms_per_step"],
+                     "scaling": s["scaling"], "config": s["config"], "roofline": s["roofline"],
+                     "gpu_launches": s["launches"], "clocks": s["clocks"]}
+    parity = parity_leg(D, pymf_b200) if not args.no_parity else None
+
+    e2e = e2e_pageable = None
     if not args.no_e2e and args.mode == "full":
-        rng = np.random.default_rng(1234 + rank)
-        if args.e2e_source == "pinned":          # page-locked host buffers (the contract's e2e source)
-            Xh = pymf_b200.pinned_empty((d, n_loc), np.float32)
-            W0 = pymf_b200.pinned_empty((d, k), np.float64)
-            H0 = pymf_b200.pinned_empty((k, n_loc), np.float64)
-            rng.random(out=Xh, dtype=np.float32)
-            rng.random(out=W0)
-            rng.random(out=H0)
-        else:                                    # ordinary pageable numpy arrays
-            Xh = rng.random((d, n_loc), dtype=np.float32)
-            W0 = rng.random((d, k))
-            H0 = rng.random((k, n_loc))
-        # Two passes of the identical user-level sequence; the second is the one reported.  The first pays this
-        # process's one-off costs for a matrix of this size (first 4 GiB device allocation and DMA mapping: measured
-        # 0.18-0.29 s vs 0.116 s, tests/_e2e_probe2.py) and is reported beside it as `first_call_seconds`.
-        rec = []
-        for _pass in range(2):
-            m = pymf_b200.NMF(Xh, num_bases=k, device=local_rank, path=args.path,
-                              process_group=(True if world > 1 else None))
-            barrier()
-            t0 = time.perf_counter()
-            m.W, m.H = W0, H0
-            m._sync_to_device()        # X / W / H host -> device (part of factorize; split out for the breakdown)
-            t1 = time.perf_counter()
-            m.factorize(niter=steps)
-            t2 = time.perf_counter()
-            _ = (m.W, m.H, m.ferr)
-            torch.cuda.synchronize()
-            t3 = time.perf_counter()
-            rec.append((max_over_ranks(t3 - t0), t1 - t0, t2 - t1, t3 - t2, bool(m._engine.last_upload_pinned)))
-            del m
-            if _pass == 0:             # fresh starting factors for the reported pass (W0 / H0 were updated in place)
-                rng = np.random.default_rng(4321 + rank)
-                W0[...] = rng.random(W0.shape)
-                H0[...] = rng.random(H0.shape)
-        t_e2e, t_up, t_it, t_dn, direct = rec[1]
-        h2d = (Xh.nbytes + W0.nbytes + H0.nbytes) / float(steps)
-        d2h = (W0.nbytes + H0.nbytes + 8 * steps) / float(steps)
-        e2e = {"value": units_per_step * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "seconds_total": t_e2e,
-               "seconds_upload": t_up, "seconds_iterations": t_it, "seconds_download": t_dn,
-               "first_call_seconds": rec[0][0],
-               "host_source": args.e2e_source, "x_upload_direct_dma": direct,
-               "numa": dict(zip(("gpu_node", "x_host_node"), pymf_b200.numa_info(Xh, local_rank))),
-               "what": "NMF(X_host).factorize(niter=%d) incl. X/W/H upload and W/H/ferr download; second of two "
-                       "identical calls in this process" % steps}
+        e2e = e2e_leg(D, pymf_b200, args, wl_name, steps, "pinned")
+        e2e_pageable = e2e_leg(D, pymf_b200, args, wl_name, steps, "pageable")
+        e2e_pageable["ratio_to_pinned"] = e2e_pageable["value"] / e2e["value"]
+        if secondary is not None:
+            secondary["e2e"] = e2e_leg(D, pymf_b200, args, "cfg2", steps, "pinned")
+            secondary["e2e_pageable"] = e2e_leg(D, pymf_b200, args, "cfg2", steps, "pageable")
 
-    # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        rate, sample, cores, sec, n_cpu = cpu_port_rate(d, n_per_gpu, k, budget_s=20.0, steps=3, warmup=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if D.rank == 0 and D.world == 1 and not args.no_cpu:
+        cpu = cpu_arm(d, n, k, budget_s=20.0, steps=3, warmup=1)
 
-    if rank == 0:
+    if D.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wl_desc + (" per GPU, n_global = %d" % n_global if not strong else ""),
-                       "mode": args.mode, "d": d, "n_local": n_loc, "n_global": n_global, "k": k, "kernel_path": path,
-                       "arithmetic": "fp32 storage; 3xTF32 tcgen05 products (tc path) or fp32 FMA (simt path); fp64 error combine",
-                       "l2": ("inputs larger than L2 (X shard = %.2f GiB), no flush needed" % (4.0 * d * n_loc / 2 ** 30))
-                       if 4.0 * d * n_loc > 2 * 126e6 else
-                       ("X shard = %.1f MB fits the 126 MB L2 and is NOT flushed between iterations: the loop re-reads "
-                        "the same matrix every step by construction (latency-bound workload, no HBM roofline claim)"
-                        % (4.0 * d * n_loc / 1e6)),
-                       "value_units": "shard-iterations/s summed over ranks" if not strong else "iterations/s of the global problem",
-                       "ferr_after": ferr_check},
-            "e2e": e2e, "gpu_launches": int(launches), "graph_replays": int(graph_replays), "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": D.world, "steps": steps,
+            "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": main["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": main["config"], "e2e": e2e, "e2e_pageable": e2e_pageable,
+            "gpu_launches": main["launches"], "graph_replays": main["graph_replays"], "clocks": main["clocks"],
+            "roofline": main["roofline"], "cpu_baseline": cpu, "secondary": secondary,
+            "parity_vs_golden": parity,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if D.dist is not None:
+        D.dist.destroy_process_group()
 
 
 def main():
@@ -378,20 +542,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default=None, choices=[None, "auto", "simt", "tc"])
     ap.add_argument("--mode", default="full", choices=sorted(MODES),
                     help="full = W, H and error every step (the BASELINE metric); h_only / w_only = serving modes")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-source", default="pinned", choices=["pinned", "pageable"],
-                    help="host memory the e2e leg reads X/W/H from (default: page-locked)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 block of the default (cfg3) line")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
-    d, n, k, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, d, n, k, desc)
+        run_reference(args, args.workload)
     else:
-        run_ours(args, d, n, k, args.workload, desc)
+        run_ours(args, args.workload)
 
 
 if __name__ == "__main__":

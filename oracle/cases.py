@@ -35,6 +35,16 @@ CASES = {
     "k128": dict(kind="hash", seed=77, d=512, n=640, k=128, niter=5, keep=[1, 5], store32=True),
     # k not a multiple of 16, d not a multiple of 128
     "k40": dict(kind="hash", seed=99, d=300, n=1000, k=40, niter=8, keep=[1, 8], store32=True),
+    # the same cfg2 prefix followed for cfg2's full 200 iterations (north_star: <= 1e-4 per iteration)
+    "cfg2_prefix_200": dict(kind="hash", seed=1234, d=4096, n=2048, k=32, niter=200, keep=[1, 50, 100, 200],
+                            store32=True),
+    # cfg3's d and k (16384 rows = 512 MMA stages = 16 TMEM segments per column tile), cfg5's d and k.
+    # W snapshots keep every 8th row (w_stride) so that the fixtures stay ~1 MB; normW / normH are of the
+    # full matrices, and the GPU tests also run the oracle live on the full factors.
+    "cfg3_d": dict(kind="hash", seed=301, d=16384, n=2048, k=128, niter=4, keep=[1, 4], store32=True, w_stride=8),
+    "cfg5_d": dict(kind="hash", seed=501, d=32768, n=1024, k=64, niter=4, keep=[1, 4], store32=True, w_stride=8),
+    # cross-rank parity case of bench.py (N > 1): 2048 columns = 256 per rank at N = 8, tensor-path shape
+    "scale_k128": dict(kind="hash", seed=801, d=1024, n=2048, k=128, niter=6, keep=[6], store32=True),
 }
 
 

@@ -73,12 +73,15 @@ def main():
     print("early stop: len(ferr) =", len(m.ferr))
 
     # ---- 3. trajectories on the parity cases ----
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 and sys.argv[1] == "only" else None
     for name, c in cases.CASES.items():
-        if not c.get("golden", True):
+        if not c.get("golden", True) or (only is not None and name not in only):
             continue
         X, W0, H0 = cases.build(name)
         ferr, nW, nH, snaps = run_steps(ref, X.astype(np.float64), W0, H0, c["k"], c["niter"],
                                         set(c["keep"]))
+        if c.get("w_stride", 1) > 1:
+            snaps = {k_: (v[::c["w_stride"]] if k_.startswith("W_") else v) for k_, v in snaps.items()}
         if c.get("store32", False):
             snaps = {k_: v.astype(np.float32) for k_, v in snaps.items()}
         np.savez(os.path.join(OUT, "traj_%s.npz" % name), ferr=ferr, normW=nW, normH=nH, **snaps)

@@ -7,9 +7,13 @@ one injected name (``xrange``, pymf/nmf.py:182).  Nothing is copied or edited.
 import importlib.util
 import os
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# baseline/_ref is the offline `pip install --target` of the unmodified reference (git-ignored, it travels
+# to the GPU box with the repo snapshot; __graft_entry__.build() creates it where /root/reference exists)
 _CANDIDATES = [
     os.environ.get("PYMF_REF", ""),
     "/root/reference/pymf/nmf.py",
+    os.path.join(_ROOT, "baseline", "_ref", "pymf", "nmf.py"),
 ]
 
 
@@ -17,6 +21,9 @@ def find_reference():
     for p in _CANDIDATES:
         if p and os.path.isfile(p):
             return p
+    import glob
+    for p in sorted(glob.glob(os.path.join(_ROOT, "baseline", "_ref", "**", "pymf", "nmf.py"), recursive=True)):
+        return p
     return None
 
 

@@ -72,6 +72,8 @@ struct FusedParams {
     int d, n_loc, n_tiles;
     int nslab, ngroups, depth, nslot, hint;
     int pf;                 // L2 prefetch distance of the A tasks in tiles of this group (0 = off)
+    const float* wmean;     // centered W (kernels_tc.cuh "centering"): column means of W and column sums of X, else null
+    const float* xsum;
     int* fault;             // mapped host memory: the watchdogs note which wait timed out before they trap
     float* dbg;             // PYMFB_TRACE builds: event log
 };
@@ -610,9 +612,11 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
 #pragma unroll
                 for (int j = 0; j < KP; ++j) __stcg(cp + j * TILE_COLS, 0.f);                    // ready for tile seq + nslot
                 if (live) {
+                    const float xs = (p.wmean != nullptr) ? __ldg(p.xsum + col) : 0.f;
 #pragma unroll
                     for (int j = 0; j < KP; ++j) {
-                        const float hn = rg[j] * cs[j];
+                        const float cj = (p.wmean != nullptr) ? fmaf(__ldg(p.wmean + j), xs, cs[j]) : cs[j];
+                        const float hn = rg[j] * cj;
                         const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                         p.Hn[(int64_t)j * p.ldh + col] = hn;
                         p.Hs[hs_index(j, col, 2 * KP)] = hh;
@@ -700,6 +704,7 @@ inline int fused_launch(FusedPlan& f, TcPlan& p, const DevState* st, const float
     fp.ldh = p.ldh; fp.d = (int)p.d; fp.n_loc = (int)p.n_loc; fp.n_tiles = f.n_tiles;
     fp.nslab = f.nslab; fp.ngroups = f.ngroups; fp.depth = f.depth; fp.nslot = f.nslot; fp.hint = f.hint;
     fp.pf = f.pf;
+    fp.wmean = p.center ? p.wmean : nullptr; fp.xsum = p.xsum;
     fp.fault = fault;
     fp.dbg = p.dbg;
 #if defined(PYMFB_TRACE)

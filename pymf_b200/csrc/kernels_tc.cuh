@@ -206,12 +206,22 @@ __host__ __device__ __forceinline__ int64_t hs_index(int j, int64_t col, int kp2
 
 constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "segments" below)
 
-// Segments.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, so a long chain of
-// accumulating MMAs drifts low by ~4.5e-8 per MMA (measured: 2.7e-5 relative after the 512 MMAs of
-// d = 4096).  Both passes therefore cut the contraction into segments of SEG_STAGES stages
-// (32 MMAs per chain): the MMA thread alternates between two TMEM buffers, and the epilogue warps
-// drain each finished segment into fp32 registers with round-to-nearest adds while the next
-// segment is being accumulated.
+// Segments.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, so a chain of n
+// accumulating MMAs over positive data comes out LOW by ~4.2e-8 * n relative (measured: 2.7e-5 after
+// the 512 MMAs of d = 4096).  Both passes therefore cut their contraction into segments: the MMA
+// thread alternates between two TMEM buffers, and the epilogue warps drain each finished segment
+// into fp32 registers with round-to-nearest adds while the next segment is being accumulated.
+//
+// The segment LENGTH matters beyond its own bias.  The update H <- H * C / D is a ratio, and W, H
+// carry a neutral direction (W * s, H / s leaves W H unchanged) with no restoring force: a bias of
+// delta_C - delta_D per iteration in C / D accumulates LINEARLY over the iterations.  With 32-MMA
+// chains for C = W^T X against the k/8-MMA chain of D = G H the cfg2 prefix drifted 1.18e-6 per
+// iteration - a pure scale, H down, W up (tests/_drift_probe.py) - i.e. 1.2e-4 after 100 iterations,
+// beyond the 1e-4 tolerance, while everything except the scale stayed at 1e-6.  Hence: the C
+// contraction uses segments of seg_c = (rows of H contracted for G H) / 32 stages, so that the C
+// chain has exactly as many MMAs as the D chain and the two biases cancel in the ratio to first order;
+// the X H^T and H H^T contractions of the W update (ratio A / (W B)) both use SEG_STAGES-stage
+// segments over column ranges that are multiples of a segment, for the same reason.
 template <int KP>
 struct HCfg {   // H-update pass
     static constexpr int NCH = 2 * KP / 32;                         // 32-column chunks of [hi | lo]
@@ -243,7 +253,8 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              int kh_rows, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+              int kh_rows, int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+    // seg_c: stages per accumulation segment of the W^T X contraction (see "Segments" above)
     // kh_rows: rows of H contracted for G H (= the padded k of the whole problem).  For k <= 128 it equals KP;
     // for k > 128 the launch handles one 128-wide block of bases: mapH spans all kh_rows rows of H, mapG is the
     // block's [G_hi | G_lo] column slice, and Hc / Hn / Hs point at the block's rows.
@@ -323,7 +334,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
-                    const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
+                    const int seg_end = (it < nd) ? min(it + seg_c, nd) : nit;
                     const uint32_t b = g & 1u;
                     mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -373,7 +384,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         // ===== epilogue warps: drain segments into registers, then the H update =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int jbase = ((warp - (NPROD + 5)) >> 2) * Cfg::NJ;   // basis columns [jbase, jbase + NJ) of this warp
-        const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
+        const int nsegC = (nd + seg_c - 1) / seg_c;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -741,7 +752,10 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+              int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
+              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum) {
+    // wmean != nullptr: the B operands are the CENTERED W / G (k_split_hilo_centered); the epilogue adds
+    // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
     // as H, written by k_gh_posneg_simt) instead of the G H accumulator
     using Cfg = TsCfg<KP>;
@@ -822,7 +836,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
-                    const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
+                    const int seg_end = (it < nd) ? min(it + seg_c, nd) : nit;
                     const uint32_t b = g & 1u;
                     TRACE_AT(mc, 8);
                     mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
@@ -905,7 +919,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         }
     } else {
         const int q = warp & 3;
-        const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
+        const int nsegC = (nd + seg_c - 1) / seg_c;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -918,11 +932,17 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             float hreg[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
+            const float xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+            float hsum = 0.f;
+            if (wmean != nullptr) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) hsum += hreg[j];
+            }
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 10);
+                if (q == 0) TRACE_AT(g * seg_c, 10);
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 11);
+                if (q == 0) TRACE_AT(g * seg_c, 11);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
@@ -939,7 +959,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 12);
+                if (q == 0) TRACE_AT(g * seg_c, 12);
                 if (lane == 0) mbar_arrive(tempty_bar(b));
             }
             {
@@ -975,7 +995,12 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
                             const float h = hreg[j0 + j];
-                            const float hn = (Dp != nullptr) ? snmf_ratio(h, creg[j0 + j], Dp[o], Dn[o]) : mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
+                            float cj = creg[j0 + j], dj = dh[j] + dl[j];
+                            if (wmean != nullptr) {
+                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
+                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+                            }
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
                             Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
@@ -1229,6 +1254,75 @@ __global__ void k_split_hilo(const DevState* __restrict__ st, const float* __res
     dst[r * 2 * kpb + kpb + c] = v - hi;
 }
 
+// ---- centering of the small operand (TS kernels, k <= 64) ------------------------------------------------
+// W^T X and G H are sums of POSITIVE products; accumulated with truncation (see "Segments") they come out low
+// by an amount that grows with the chain length.  The TS H-update kernels therefore contract against the
+// CENTERED operand W' = W - 1 w_mean^T (column means) resp. G' = G - 1 g_mean^T: the products change sign,
+// the truncation errors stop being one-sided, and the exact identity
+//     W^T x_c = W'^T x_c + w_mean * sum_r x_rc ,     G h_c = G'^T h_c + g_mean * sum_i h_ic
+// is restored in the epilogue with one FMA per output (column sums of X are computed once per data set, those of
+// the H tile come from the registers that already hold it).  Measured on the cfg2 prefix: scale drift of W / H per
+// iteration 1.2e-6 -> see DESIGN.md 5.1.
+constexpr int CM_SPLITS = 64;          // row splits of the column-sum reduction of W
+
+// part[split][c] = sum of src[r][c] over the rows of the split (c < cols <= 64; deterministic order)
+__global__ void __launch_bounds__(256)
+k_colsum_partial(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int ld, int cols,
+                 float* __restrict__ part) {
+    if (st->stop) return;
+    __shared__ float sh[256];
+    const int lanes = 256 / cols;                 // row lanes per block (cols = 32 or 64)
+    const int c = threadIdx.x % cols, rl = threadIdx.x / cols;
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+    float acc = 0.f;
+    for (int64_t r = r0 + rl; r < r1; r += lanes) acc += src[r * ld + c];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0) {
+        for (int l = 1; l < lanes; ++l) acc += sh[l * cols + c];
+        part[blockIdx.x * cols + c] = acc;
+    }
+}
+
+// [hi | lo] split of (src - column mean): mean[c] = (sum over the `nsplit` partials) / rows_real, also written to
+// mean_out by block 0; rows >= rows_real and columns >= cols_real stay 0 (zero padding must stay exact).
+__global__ void __launch_bounds__(256)
+k_split_hilo_centered(const DevState* __restrict__ st, const float* __restrict__ src, int64_t rows, int ld, int kpb,
+                      const float* __restrict__ part, int nsplit, int64_t rows_real, int cols_real,
+                      float* __restrict__ dst, float* __restrict__ mean_out) {
+    if (st->stop) return;
+    __shared__ float mean[64];
+    if (threadIdx.x < kpb) {
+        float a = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) a += part[sp * kpb + threadIdx.x];
+        a = (threadIdx.x < cols_real) ? a / (float)rows_real : 0.f;
+        mean[threadIdx.x] = a;
+        if (blockIdx.x == 0) mean_out[threadIdx.x] = a;
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * kpb; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / kpb;
+        const int c = (int)(i % kpb);
+        const float v = (r < rows_real && c < cols_real) ? src[r * ld + c] - mean[c] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        dst[r * 2 * kpb + c] = hi;
+        dst[r * 2 * kpb + kpb + c] = v - hi;
+    }
+}
+
+// xsum[c] = sum over the rows of X of column c (fp64 accumulation, stored fp32); once per data set
+__global__ void __launch_bounds__(256)
+k_colsum_x(const float* __restrict__ X, int64_t ldx, int64_t d, int64_t n_loc, float* __restrict__ xsum) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_loc) return;
+    double a0 = 0.0, a1 = 0.0;
+    int64_t r = 0;
+    for (; r + 1 < d; r += 2) { a0 += (double)X[r * ldx + c]; a1 += (double)X[(r + 1) * ldx + c]; }
+    if (r < d) a0 += (double)X[r * ldx + c];
+    xsum[c] = (float)(a0 + a1);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -1259,6 +1353,13 @@ struct TcPlan {
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
     const float* Dp = nullptr; // Semi-NMF: G+ H and G- H of the H buffer being updated (set by the scheduler), else null
     const float* Dn = nullptr;
+    bool center = false;       // TS kernels: contract against the centered W / G (see "centering" above)
+    float* xsum = nullptr;     // n_loc column sums of X (center)
+    bool xsum_valid = false;
+    float* wmean = nullptr;    // kp column means of W, kp column means of G, CM_SPLITS x kp partials
+    float* gmean = nullptr;
+    float* cm_part = nullptr;
+    int seg_c = 1;             // stages per segment of the W^T X contraction (= kp / 32: the G H chain length)
     float lam_h = 0.f;         // BNMF penalty weight of the next H-update launch (0 = plain NMF), set by the scheduler
     std::string err;
 };
@@ -1364,6 +1465,9 @@ inline void tc_release(TcPlan& p) {
 #endif
     if (p.Wsplit) cudaFree(p.Wsplit);
     if (p.Gsplit) cudaFree(p.Gsplit);
+    if (p.xsum) cudaFree(p.xsum);
+    if (p.wmean) cudaFree(p.wmean);
+    p.xsum = p.wmean = p.gmean = p.cm_part = nullptr; p.xsum_valid = false; p.center = false;
     for (int i = 0; i < 2; ++i) { if (p.Hs[i]) cudaFree(p.Hs[i]); p.Hs[i] = nullptr; p.hs_valid[i] = false; }
     p.Wsplit = p.Gsplit = nullptr;
     p.ready = false;
@@ -1417,6 +1521,21 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     }
 #endif
     p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
+    {   // Bias of the H-update ratio C / D (see "Segments"): the TS kernels (k <= 64) contract against centered
+        // operands and keep SEG_STAGES-stage segments; the SS kernels give the C chain the D chain's length.
+        // PYMFB_SEG_C / PYMFB_CENTER override both for experiments.
+        const char* e = getenv("PYMFB_SEG_C");
+        const char* ce = getenv("PYMFB_CENTER");
+        p.center = p.use_ts && !(ce && ce[0] == '0');
+        p.seg_c = (e && atoi(e) > 0) ? atoi(e) : (p.center ? tc::SEG_STAGES : std::max(1, kp / tc::R1));
+        if (p.center) {
+            if (cudaMalloc(&p.xsum, (size_t)n_loc * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc xsum failed"; return 1; }
+            if (cudaMalloc(&p.wmean, (size_t)(2 + tc::CM_SPLITS) * kp * sizeof(float)) != cudaSuccess) { p.err = "cudaMalloc wmean failed"; return 1; }
+            p.gmean = p.wmean + kp;
+            p.cm_part = p.wmean + 2 * kp;
+            p.xsum_valid = false;
+        }
+    }
     // X H^T tasks: (row block, column range); ~4 tasks per SM, each a multiple of 32 columns
     p.x_rb = (int)((d + 127) / 128);
     const int64_t chunks = (n_loc + 31) / 32;
@@ -1437,13 +1556,17 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         }
     }
     splits = std::min(splits, chunks);
-    const int64_t chunks_per = (chunks + splits - 1) / splits;
+    // Column ranges are whole segments (SEG_STAGES stages) wherever n allows, for X H^T and H H^T alike: the W update
+    // is the ratio A / (W B), so the accumulation chains of A and B must have the same length (see "Segments").
+    auto seg_round = [&](int64_t per) { return (per >= tc::SEG_STAGES) ? (per + tc::SEG_STAGES - 1) / tc::SEG_STAGES * tc::SEG_STAGES : per; };
+    const int64_t chunks_per = seg_round((chunks + splits - 1) / splits);
     p.x_cols_per_task = (int)(chunks_per * 32);
     splits = (chunks + chunks_per - 1) / chunks_per;
     p.x_tasks = (int)(splits * p.x_rb);
-    {   // H H^T tasks (TS kernels): ~one short task per SM
+    {   // H H^T tasks (TS kernels): ~one short task per SM, never shorter than the X H^T chains
         int64_t hsplits = std::min<int64_t>(chunks, sm_count);
-        const int64_t hper = (chunks + hsplits - 1) / hsplits;
+        int64_t hper = seg_round((chunks + hsplits - 1) / hsplits);
+        if (hper < tc::SEG_STAGES) hper = std::min<int64_t>(chunks_per, tc::SEG_STAGES);
         p.hh_cols_per_task = (int)(hper * 32);
         p.hh_tasks = (int)((chunks + hper - 1) / hper);
     }
@@ -1454,6 +1577,21 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
 // refresh [W_hi | W_lo] and [G_hi | G_lo] after W / G changed
 inline int tc_after_gram(TcPlan& p, const DevState* st, const float* W, const float* G, cudaStream_t stream, int64_t* launches) {
     const int64_t nw = p.d * p.kpb, ng = (int64_t)p.kp * p.kpb;
+    if (p.center) {        // nblk == 1, kpb == kp
+        if (!p.xsum_valid) {
+            tc::k_colsum_x<<<(unsigned)((p.n_loc + 255) / 256), 256, 0, stream>>>(p.X, p.ldx, p.d, p.n_loc, p.xsum);
+            p.xsum_valid = true;
+            *launches += 1;
+        }
+        const int wsplits = (int)std::min<int64_t>(tc::CM_SPLITS, std::max<int64_t>(1, p.d / 64));
+        tc::k_colsum_partial<<<wsplits, 256, 0, stream>>>(st, W, p.d, p.kp, p.kp, p.cm_part);
+        tc::k_split_hilo_centered<<<(unsigned)std::min<int64_t>((nw + 255) / 256, 4 * p.sm_count), 256, 0, stream>>>(
+            st, W, p.d, p.kp, p.kp, p.cm_part, wsplits, p.d, p.k, p.Wsplit, p.wmean);
+        // G: kp x kp, one block: the "partials" are the rows of G themselves (rows >= k are zero)
+        tc::k_split_hilo_centered<<<1, 256, 0, stream>>>(st, G, p.kp, p.kp, p.kp, G, p.kp, p.k, p.k, p.Gsplit, p.gmean);
+        *launches += 3;
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     for (int b = 0; b < p.nblk; ++b) {
         tc::k_split_hilo<<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(st, W, p.d, p.kp, b * p.kpb, p.kpb, p.Wsplit + (size_t)b * p.d * 2 * p.kpb);
         tc::k_split_hilo<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(st, G, p.kp, p.kp, b * p.kpb, p.kpb, p.Gsplit + (size_t)b * p.kp * 2 * p.kpb);
@@ -1469,7 +1607,7 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
         const size_t hoff = (size_t)b * p.kpb * p.ldh;
         tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_h, p.mapW_b[b], p.mapH_h[hsrc], p.mapG_b[b], st, p.Hbuf[hsrc] + hoff, Hn + hoff, p.Hs[hsrc ^ 1] + 2 * hoff,
-            p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.lam_h,
+            p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.seg_c, p.lam_h,
             p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr);
     }
 }
@@ -1482,7 +1620,8 @@ template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = grid_cap(std::min(p.h_tiles, p.sm_count));
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
-        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.lam_h, p.Dp, p.Dn);
+        p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.seg_c, p.lam_h, p.Dp, p.Dn,
+        p.center ? p.wmean : nullptr, p.gmean, p.xsum);
 }
 template <int KP>
 inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {

@@ -90,7 +90,10 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+              int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
+              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum) {
+    // wmean != nullptr: the B operands are the CENTERED W / G (k_split_hilo_centered); the epilogue adds
+    // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
     // as H, written by k_gh_posneg_simt) instead of the G H accumulator
     using Cfg = Ts2Cfg<KP>;
@@ -181,7 +184,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 const int tile = 2 * sup + (int)rank; (void)tile;
                 int it = 0;
                 while (it < nit) {
-                    const int seg_end = (it < nd) ? min(it + SEG_STAGES, nd) : nit;
+                    const int seg_end = (it < nd) ? min(it + seg_c, nd) : nit;
                     const uint32_t b = g & 1u;
                     TRACE_AT(mc, 8);
                     TS2_WAIT(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
@@ -253,7 +256,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         }
     } else {
         const int q = warp & 3;
-        const int nsegC = (nd + SEG_STAGES - 1) / SEG_STAGES;
+        const int nsegC = (nd + seg_c - 1) / seg_c;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int sup = pair; sup < nsuper; sup += npairs) {
@@ -267,11 +270,17 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             float hreg[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
+            const float xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+            float hsum = 0.f;
+            if (wmean != nullptr) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) hsum += hreg[j];
+            }
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 10);
+                if (q == 0) TRACE_AT(g * seg_c, 10);
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 11);
+                if (q == 0) TRACE_AT(g * seg_c, 11);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
@@ -288,7 +297,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (q == 0) TRACE_AT(g * SEG_STAGES, 12);
+                if (q == 0) TRACE_AT(g * seg_c, 12);
                 if (lane == 0) mbar_arrive_cluster(tempty_bar(b), 0);
             }
             {
@@ -324,7 +333,12 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
                             const float h = hreg[j0 + j];
-                            const float hn = (Dp != nullptr) ? snmf_ratio(h, creg[j0 + j], Dp[o], Dn[o]) : mu_ratio(h, creg[j0 + j], dh[j] + dl[j], lam);
+                            float cj = creg[j0 + j], dj = dh[j] + dl[j];
+                            if (wmean != nullptr) {
+                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
+                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+                            }
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
                             Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
@@ -370,11 +384,11 @@ inline int ts2_h_update(TcPlan& p, const DevState* st, const float* Hc, float* H
     if (p.kp == 64)
         tc::k_h_update_ts2<64><<<grid, tc::Ts2Cfg<64>::THREADS, tc::Ts2Cfg<64>::SMEM_BYTES, stream>>>(
             p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
-            p.lam_h, p.Dp, p.Dn);
+            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum);
     else
         tc::k_h_update_ts2<32><<<grid, tc::Ts2Cfg<32>::THREADS, tc::Ts2Cfg<32>::SMEM_BYTES, stream>>>(
             p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
-            p.lam_h, p.Dp, p.Dn);
+            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum);
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -95,6 +95,12 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    // optional (NCCL >= 2.19): user-buffer registration, so that the all-reduce runs in place on the buffer the
+    // pass epilogues write (zero-copy / NVLS-capable) instead of staging through NCCL's own buffers
+    int (*MemAlloc)(void**, size_t) = nullptr;
+    int (*MemFree)(void*) = nullptr;
+    int (*CommRegister)(void*, void*, size_t, void**) = nullptr;
+    int (*CommDeregister)(void*, void*) = nullptr;
 };
 }  // namespace
 static NcclApi g_nccl;
@@ -112,6 +118,10 @@ static int nccl_load() {
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    g_nccl.MemAlloc = (int (*)(void**, size_t))dlsym(h, "ncclMemAlloc");
+    g_nccl.MemFree = (int (*)(void*))dlsym(h, "ncclMemFree");
+    g_nccl.CommRegister = (int (*)(void*, void*, size_t, void**))dlsym(h, "ncclCommRegister");
+    g_nccl.CommDeregister = (int (*)(void*, void*))dlsym(h, "ncclCommDeregister");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
         return fail("libnccl is missing required symbols");
     g_nccl.lib = h;
@@ -153,8 +163,10 @@ struct pymfb_ctx {
     int64_t ldh = 0;
     bool w_set = false, h_set = false;
 
-    float* P = nullptr;            // local partials [A (d x kp) | B (kp x kp)]
-    float* AB = nullptr;           // reduced (== P when world == 1)
+    float* P = nullptr;            // [A (d x kp) | B (kp x kp)]: local partials, all-reduced IN PLACE over the ranks
+    float* AB = nullptr;           // alias of P (the reduced values)
+    bool p_nccl = false;           // P comes from ncclMemAlloc and is registered with the communicator
+    void* p_reg = nullptr;         // ncclCommRegister handle
     int64_t ab_count = 0;
     float* G = nullptr;            // kp x kp
     float* Gpart = nullptr;        // g_splits x kp x kp
@@ -188,6 +200,7 @@ struct pymfb_ctx {
     int world = 1, rank = 0;
 
     int64_t launches = 0;
+    bool uw_smem_set = false;      // k_update_w's dynamic shared memory attribute raised (k > 1536)
     bool last_upload_pinned = false;
     void* stage = nullptr;         // factor transfer staging (factor_stage)
     size_t stage_bytes = 0;
@@ -308,6 +321,11 @@ static int launch_update_w(pymfb_ctx* c) {
     const float* B = c->AB + c->d * c->kp;
     unsigned grid = (unsigned)((c->d + UW_ROWS - 1) / UW_ROWS);
     size_t smem = (size_t)UW_ROWS * c->kp * sizeof(float);
+    if (smem > 48 * 1024 && !c->uw_smem_set) {     // k > 1536: beyond the default dynamic shared-memory limit
+        CU(cudaFuncSetAttribute(k_update_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_update_w_snmf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->uw_smem_set = true;
+    }
     if (c->variant == PYMFB_VARIANT_SNMF) {      // W = A B^-1 (pymf/snmf.py:67-70); the old W is not an input
         k_inv_f64<<<1, 256, 0, c->stream>>>(c->st, B, c->kp, c->k, c->inv_work, c->Binv);
         k_update_w_snmf<<<grid, SIMT_THREADS, smem, c->stream>>>(c->st, A, c->Binv, c->W[c->wcur ^ 1], c->d, c->kp, c->k);
@@ -379,7 +397,7 @@ static int launch_fused(pymfb_ctx* c) {
     CK(timing_end(c, 0, e0, e1));
     c->hcur ^= 1;
     if (c->world > 1)
-        NC(g_nccl.AllReduce(c->P, c->AB, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
+        NC(g_nccl.AllReduce(c->P, c->P, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
     c->ab_valid = true;
     return 0;
 }
@@ -424,7 +442,7 @@ static int launch_xht(pymfb_ctx* c) {
     }
     CK(timing_end(c, 1, e0, e1));
     if (c->world > 1)
-        NC(g_nccl.AllReduce(c->P, c->AB, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
+        NC(g_nccl.AllReduce(c->P, c->P, (size_t)c->ab_count, kNcclFloat32, kNcclSum, c->comm, c->stream));
     c->ab_valid = true;
     return 0;
 }
@@ -509,11 +527,13 @@ static void graph_drop(pymfb_ctx* c) {
 
 // Launch-bound problems (an iteration is ~10 kernels of a few microseconds each: cfg1 1000 x 500 ran 108 us per
 // iteration, almost all of it launch gaps) replay TWO iterations - one full ping-pong period of the W / H buffers -
-// as one CUDA graph.  Eligible: single rank, plain NMF (the BNMF weight changes every iteration), no per-kernel
-// timing, small X.  The graph is captured from the steady state (after two plain iterations) and cached.
+// as one CUDA graph.  Eligible: plain NMF (the BNMF weight changes every iteration), no per-kernel timing, small X;
+// any number of ranks - the in-place ncclAllReduce of [X H^T | H H^T] is captured with the kernels (every rank
+// replays the same sequence of collectives; the plain warm-up iterations before the capture have already set up
+// NCCL's connections).  The graph is captured from the steady state (after two plain iterations) and cached.
 static bool graph_eligible(const pymfb_ctx* c, int niter) {
     if (c->graph_opt == PYMFB_GRAPH_OFF) return false;
-    if (c->world > 1 || c->timing || c->lam_w != 0.0 || c->lam_h != 0.0 || niter < 5) return false;
+    if (c->timing || c->lam_w != 0.0 || c->lam_h != 0.0 || niter < 5) return false;
     if (c->path == PYMFB_PATH_TC && c->fused.ready) return false;
     if (c->graph_opt == PYMFB_GRAPH_ON) return true;
     return (double)c->d * (double)c->n_loc <= 16777216.0;
@@ -575,6 +595,12 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
     return 0;
 }
 
+static int p_unregister(pymfb_ctx* c) {
+    if (c->p_reg && c->comm && g_nccl.CommDeregister) g_nccl.CommDeregister(c->comm, c->p_reg);
+    c->p_reg = nullptr;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -603,6 +629,10 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     CU(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
     CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     if (cc_major != 10) return fail("device %d is sm_%d%d; libpymfb is built for sm_100a (B200) only", device, cc_major, cc_minor);
+    {   // the W-update kernels stage UW_ROWS rows of A (UW_ROWS x kp fp32) in dynamic shared memory
+        const int64_t kp_max = (int64_t)(227 * 1024) / (UW_ROWS * (int64_t)sizeof(float)) / 32 * 32;
+        if ((int64_t)k > kp_max) return fail("k = %d is beyond the supported bound (k <= %lld: one row block of the W update must fit shared memory)", k, (long long)kp_max);
+    }
     pymfb_ctx* c = new pymfb_ctx();
     c->device = device; c->d = d; c->n_loc = n_local; c->n_glob = n_global; c->col0 = col0; c->k = k;
     // k is zero-padded to kp (exact: padded rows / columns of W and H stay 0 under the updates).  Small k on a
@@ -624,7 +654,7 @@ int pymfb_create(pymfb_ctx** out, int device, int64_t d, int64_t n_local, int64_
     c->ab_count = d * c->kp + (int64_t)c->kp * c->kp;
     CU(cudaMalloc(&c->P, c->ab_count * sizeof(float)));
     CU(cudaMemsetAsync(c->P, 0, c->ab_count * sizeof(float), c->stream));
-    c->AB = c->P;   // separate buffer is allocated by pymfb_comm_init
+    c->AB = c->P;   // reduced in place (comm_bind may move it into NCCL-registered memory)
     CU(cudaMalloc(&c->G, (size_t)c->kp * c->kp * sizeof(float)));
     // row splits of the W^T W reduction: enough CTAs to cover the SMs, >= 64 rows each
     {
@@ -669,14 +699,15 @@ int pymfb_destroy(pymfb_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->comm && c->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     graph_drop(c);
+    p_unregister(c);
+    if (c->comm && c->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     tc_release(c->tc);
     fused_release(c->fused);
     for (int w = 0; w < 2; ++w)
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    if (c->AB != c->P) cudaFree(c->AB);
-    cudaFree(c->P); cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
+    if (c->p_nccl && g_nccl.MemFree) g_nccl.MemFree(c->P); else cudaFree(c->P);
+    cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
     cudaFree(c->h_cpart); cudaFree(c->h_tickets);
     cudaFree(c->Gpos); cudaFree(c->Gneg); cudaFree(c->Dp); cudaFree(c->Dn); cudaFree(c->inv_work); cudaFree(c->Binv);
     cudaFree(c->stage); cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
@@ -760,13 +791,27 @@ int pymfb_comm_unique_id(void* out128) {
 }
 
 static int comm_bind(pymfb_ctx* c, void* comm, bool owned, int world, int rank) {
+    CK(p_unregister(c));                      // from the previous communicator, while it still exists
     if (c->comm && c->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->comm = comm; c->comm_owned = owned;
     c->world = world; c->rank = rank;
-    if (c->AB == c->P) {
-        CU(cudaMalloc(&c->AB, c->ab_count * sizeof(float)));
-        CU(cudaMemset(c->AB, 0, c->ab_count * sizeof(float)));
+    // [X H^T | H H^T] lives in ONE buffer that the pass epilogues write and ncclAllReduce reduces in place.  With
+    // a registration-capable NCCL the buffer comes from ncclMemAlloc and is registered with the communicator
+    // (PYMFB_NCCL_REG=0 keeps the plain cudaMalloc buffer).
+    const char* e = getenv("PYMFB_NCCL_REG");
+    const bool want_reg = !(e && e[0] == '0') && g_nccl.MemAlloc && g_nccl.MemFree && g_nccl.CommRegister && g_nccl.CommDeregister;
+    if (want_reg) {
+        void* np = nullptr;
+        if (!c->p_nccl && g_nccl.MemAlloc(&np, c->ab_count * sizeof(float)) == 0 && np) {
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaFree(c->P));
+            c->P = c->AB = (float*)np;
+            c->p_nccl = true;
+            CU(cudaMemset(c->P, 0, c->ab_count * sizeof(float)));
+        }
+        if (c->p_nccl && g_nccl.CommRegister(comm, c->P, c->ab_count * sizeof(float), &c->p_reg) != 0) c->p_reg = nullptr;
     }
+    c->p_zeroed = false;
     graph_drop(c); c->graph_key = 0;
     c->ab_valid = false; c->xx_valid = false;
     return 0;
@@ -1244,6 +1289,8 @@ int pymfb_frobenius(pymfb_ctx* c, double* out) {
 }
 
 int pymfb_enqueue(pymfb_ctx* c, int niter, unsigned flags) {
+    CK(check_ready(c));
+    if (niter < 0) return fail("niter < 0");
     if (flags & PYMFB_EARLY_STOP) return fail("pymfb_enqueue does not support PYMFB_EARLY_STOP (use pymfb_run)");
     if ((flags & PYMFB_COMPUTE_ERR) && niter > c->ferr_cap) {
         CU(cudaSetDevice(c->device));

@@ -16,6 +16,7 @@ Differences that are deliberate and documented in DESIGN.md:
 """
 import logging
 import sys
+import time
 
 import numpy as np
 
@@ -44,12 +45,13 @@ class _Factor(object):
     ``dev_newer``  the device copy holds newer values than ``host``
     ``host_dirty`` ``host`` may hold values the device has not seen (assigned, or handed out)
     """
-    __slots__ = ("host", "dev_newer", "host_dirty")
+    __slots__ = ("host", "dev_newer", "host_dirty", "user_owned")
 
-    def __init__(self, host):
+    def __init__(self, host, user_owned=False):
         self.host = host
         self.dev_newer = False
         self.host_dirty = True
+        self.user_owned = user_owned      # the caller holds a reference to `host`: keep it current (in-place contract)
 
 
 class NMF(object):
@@ -90,6 +92,7 @@ class NMF(object):
         self._engine = None
         self._x_uploaded = False
         self._factors = {}
+        self.timings = {}                                      # seconds of the last factorize(): upload_s, iterate_s, download_s
         self._data = data                                      # by reference, :93
         self._num_bases = num_bases                            # :94
         (self._data_dimension, n_local) = self._data.shape     # :97
@@ -163,19 +166,26 @@ class NMF(object):
         if f is None:
             raise AttributeError("'NMF' object has no attribute '%s'" % name)
         if f.dev_newer:
-            eng = self._engine
-            fresh = (eng.get_w(np.float64, out=f.host) if name == "W"
-                     else eng.get_h(np.float64, out=f.host))
-            if fresh is not f.host:
-                f.host[...] = fresh                   # in place: `mdl.W is W` stays true
-            f.dev_newer = False
-        f.host_dirty = True                           # handed out: the caller may mutate it
+            self._download(name, f)
+        # Handed out: the caller may mutate it in place (mdl.W[...] = ...), which cannot be observed, so the
+        # next device call re-uploads this factor.  An exact change check (keep a copy + compare) costs as
+        # much host bandwidth as the upload it would save.
+        f.host_dirty = True
         return f.host
 
+    def _download(self, name, f):
+        eng = self._engine
+        fresh = (eng.get_w(np.float64, out=f.host) if name == "W"
+                 else eng.get_h(np.float64, out=f.host))
+        if fresh is not f.host:
+            f.host[...] = fresh                       # in place: `mdl.W is W` stays true
+        f.dev_newer = False
+
     def _set_factor(self, name, value):
-        if not (isinstance(value, np.ndarray) and value.dtype.kind == "f" and value.flags.writeable):
+        user_owned = isinstance(value, np.ndarray) and value.dtype.kind == "f" and value.flags.writeable
+        if not user_owned:
             value = np.array(value, dtype=np.float64)
-        self._factors[name] = _Factor(value)
+        self._factors[name] = _Factor(value, user_owned)
 
     W = property(lambda self: self._get_factor("W"), lambda self, v: self._set_factor("W", v),
                  lambda self: self._factors.pop("W", None))
@@ -219,6 +229,8 @@ class NMF(object):
 
     def _sync_to_device(self):
         eng = self._ensure_engine()
+        if self._world > 1:
+            self._replicate_w()
         for name, setter in (("W", eng.set_w), ("H", eng.set_h)):
             f = self._factors.get(name)
             if f is not None and f.host_dirty:
@@ -226,6 +238,31 @@ class NMF(object):
                 f.host_dirty = False
                 f.dev_newer = False
         return eng
+
+    def _replicate_w(self):
+        """W is REPLICATED across the ranks of the process group, but every rank draws (init_w) or is handed
+        its own host copy.  Before any rank uploads a host-side W, rank 0's values are broadcast into every
+        rank's array (in place), so the replicas start bit-identical whether or not the caller seeded numpy
+        identically.  Collective: all ranks decide together (one small all-reduce of the dirty flags)."""
+        import torch
+        dist = self._dist()
+        g = self._group()
+        f = self._factors.get("W")
+        backend = str(dist.get_backend(g))
+        dev = torch.device("cuda", self._device) if "nccl" in backend else torch.device("cpu")
+        flag = torch.tensor([1 if (f is not None and f.host_dirty) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=g)
+        if int(flag.item()) == 0:
+            return
+        if f is None:
+            raise RuntimeError("W is set on some ranks of the process group but not on this one")
+        if f.dev_newer:                                          # this rank's current values live on the device
+            self._get_factor("W")
+        src = dist.get_global_rank(g, 0) if g is not None else 0
+        t = torch.from_numpy(np.ascontiguousarray(f.host, dtype=np.float64)).to(dev)
+        dist.broadcast(t, src=src, group=g)
+        f.host[...] = t.cpu().numpy()
+        f.host_dirty = True
 
     def _mark_device_newer(self, name):
         f = self._factors[name]
@@ -243,9 +280,13 @@ class NMF(object):
 
     def init_h(self):                                                    # pymf/nmf.py:119-120
         if self._world > 1:
-            # same stream as a single-process run with the same seed: draw all of H, keep our columns
-            full = np.random.random((self._num_bases, self._num_samples))
-            self.H = np.ascontiguousarray(full[:, self._col0:self._col0 + self._n_local])
+            # Same stream as a single-process run with the same seed (element (j, c) is draw j * n + c of numpy's
+            # global generator, which cannot skip ahead): one ROW of the global H at a time, keeping our columns,
+            # so a rank never holds more than its own k x n_local block plus one row.
+            H = np.empty((self._num_bases, self._n_local))
+            for j in range(self._num_bases):
+                H[j] = np.random.random(self._num_samples)[self._col0:self._col0 + self._n_local]
+            self.H = H
         else:
             self.H = np.random.random((self._num_bases, self._num_samples))
 
@@ -292,13 +333,24 @@ class NMF(object):
         if self._hooks_overridden():
             return self._factorize_template(niter, compute_w, compute_h, compute_err)
 
+        t0 = time.perf_counter()
         eng = self._sync_to_device()
+        t1 = time.perf_counter()
         ferr, done = eng.run(niter, compute_w=compute_w, compute_h=compute_h,
                              compute_err=compute_err, early_stop=True)
+        t2 = time.perf_counter()
         if compute_w and done > 0:
             self._mark_device_newer("W")
         if compute_h and done > 0:
             self._mark_device_newer("H")
+        # The reference updates W / H in place (pymf/nmf.py:125-126,131-132): an array the caller assigned and
+        # still holds must show the new values after factorize() returns, not only after `.W` is read again.
+        # Arrays this object created itself are brought back lazily, on first read.
+        for name in ("W", "H"):
+            f = self._factors[name]
+            if f.user_owned and f.dev_newer:
+                self._download(name, f)
+        self.timings = {"upload_s": t1 - t0, "iterate_s": t2 - t1, "download_s": time.perf_counter() - t2}
         if compute_err:
             full = np.zeros(niter)                                                # :179-180
             full[:len(ferr)] = ferr

@@ -12,6 +12,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a B200 (or without the built library) the gpu-marked tests are skipped, not failed, so a plain
+    `pytest tests` on a CPU-only box is green.  (The product itself still raises: there is no CPU path.)"""
+    try:
+        from pymf_b200 import _lib
+        have_gpu = _lib.device_count() > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a B200 and the built libpymfb.so")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

@@ -49,17 +49,76 @@ def test_trajectory_matches_reference_golden(name, err_mode, golden_dir):
             e.set_w(W0)
             e.set_h(H0)
             ferr = np.zeros(c["niter"])
+            ws = c.get("w_stride", 1)              # large-d fixtures keep every ws-th row of W + the full norms
             for i in range(c["niter"]):
                 f, done = e.run(1, early_stop=False)
                 ferr[i] = f[0]
                 if (i + 1) in c["keep"]:
-                    assert rel(e.get_w(), g["W_%d" % (i + 1)]) < TOL_WH, (name, path, i)
+                    W = e.get_w()
+                    assert rel(W[::ws], g["W_%d" % (i + 1)]) < TOL_WH, (name, path, i)
+                    assert abs(np.linalg.norm(W) - g["normW"][i]) / g["normW"][i] < TOL_WH, (name, path, i)
                     assert rel(e.get_h(), g["H_%d" % (i + 1)]) < TOL_WH, (name, path, i)
             assert np.max(np.abs(ferr - g["ferr"]) / g["ferr"]) < TOL_FERR, (name, path)
             # Frobenius norms of W/H per iteration are not available from single-stepping only at
             # kept iterations; the final ones are checked through get_w/get_h above.
         finally:
             e.close()
+
+
+def test_200_iteration_trajectory_on_the_tensor_path(golden_dir):
+    """north_star: per-iteration W/H within 1e-4 over cfg2's 200 iterations.  The cfg2 column prefix
+    (4096 x 2048, k = 32) on the tcgen05 path, run as multi-iteration enqueues (the product's code path:
+    one pymfb_run per segment, A/B carried across iterations) against the reference's trajectory: ferr
+    at every one of the 200 iterations, W/H at iterations 1, 50, 100 and 200."""
+    c = cases.CASES["cfg2_prefix_200"]
+    g = np.load(os.path.join(golden_dir, "traj_cfg2_prefix_200.npz"))
+    X, W0, H0 = cases.build("cfg2_prefix_200")
+    e = pymf_b200.Engine(c["d"], c["n"], c["k"], path="tc")
+    try:
+        e.set_err_mode("trace")
+        e.upload_x(X); e.set_w(W0); e.set_h(H0)
+        ferr, at, worst = [], 0, 0.0
+        for stop in c["keep"]:
+            f, done = e.run(stop - at, early_stop=False)
+            assert done == stop - at
+            ferr.extend(f)
+            at = stop
+            rw, rh = rel(e.get_w(), g["W_%d" % stop]), rel(e.get_h(), g["H_%d" % stop])
+            worst = max(worst, rw, rh)
+            assert rw < TOL_WH and rh < TOL_WH, (stop, rw, rh)
+        assert e.active_path == "tc"
+        ferr = np.array(ferr)
+        assert ferr.shape == (200,)
+        assert np.max(np.abs(ferr - g["ferr"]) / g["ferr"]) < TOL_FERR
+        print("200-iteration tc trajectory: worst rel W/H %.2e, worst rel ferr %.2e"
+              % (worst, np.max(np.abs(ferr - g["ferr"]) / g["ferr"])))
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("shape", [(16384, 2048, 128), (32768, 1024, 64), (16384, 1280, 32)])
+def test_large_d_matches_live_oracle(shape):
+    """cfg3's (d = 16384, k = 128) and cfg5's (d = 32768, k = 64) contraction depth against the float64
+    oracle run live on the FULL factors (the committed cfg3_d / cfg5_d fixtures hold every 8th row of W):
+    512 / 1024 MMA stages per column tile, i.e. 16 / 32 TMEM segments drained with RN adds."""
+    d, n, k = shape
+    X = O.gen_matrix(d + 1, d, n)
+    W0 = O.gen_matrix(d + 2, d, k).astype(np.float64)
+    H0 = O.gen_matrix(d + 3, k, n).astype(np.float64)
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=3, early_stop=False)
+    e = pymf_b200.Engine(d, n, k, path="tc")
+    try:
+        e.set_err_mode("trace")
+        e.upload_x(X); e.set_w(W0); e.set_h(H0)
+        f, done = e.run(3, early_stop=False)
+        rw, rh = rel(e.get_w(), Wr), rel(e.get_h(), Hr)
+        assert rw < TOL_WH and rh < TOL_WH, (rw, rh)
+        assert np.max(np.abs(f - fr) / fr) < TOL_FERR
+        e.set_err_mode("direct")
+        assert abs(e.frobenius() - fr[-1]) / fr[-1] < TOL_FERR
+    finally:
+        e.close()
 
 
 @pytest.mark.parametrize("name", ["cfg1", "ragged", "k40"])
