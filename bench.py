@@ -499,23 +499,26 @@ def run_ours(args, wl_name):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     d, n, k, scaling, desc = WORKLOADS[wl_name]
 
-    main = device_leg(D, pymf_b200, args, wl_name, steps, warmup, args.mode)
+    # The cfg2 block runs FIRST: cfg3 is tensor-bound and drives the GPU into its power cap, and a memory-bound
+    # run started right after it inherits the reduced clocks (measured: 1.52 vs 1.40 ms per cfg2 iteration).
     secondary = None
     if wl_name == "cfg3" and args.mode == "full" and not args.no_secondary:
         s = device_leg(D, pymf_b200, args, "cfg2", steps, warmup, "full")
         secondary = {"metric": METRIC, "value": s["value"], "unit": UNIT, "ms_per_step": s["ms_per_step"],
                      "scaling": s["scaling"], "config": s["config"], "roofline": s["roofline"],
                      "gpu_launches": s["launches"], "clocks": s["clocks"]}
+    main = device_leg(D, pymf_b200, args, wl_name, steps, warmup, args.mode)
     parity = parity_leg(D, pymf_b200) if not args.no_parity else None
 
     e2e = e2e_pageable = None
     if not args.no_e2e and args.mode == "full":
-        e2e = e2e_leg(D, pymf_b200, args, wl_name, steps, "pinned")
-        e2e_pageable = e2e_leg(D, pymf_b200, args, wl_name, steps, "pageable")
-        e2e_pageable["ratio_to_pinned"] = e2e_pageable["value"] / e2e["value"]
         if secondary is not None:
             secondary["e2e"] = e2e_leg(D, pymf_b200, args, "cfg2", steps, "pinned")
             secondary["e2e_pageable"] = e2e_leg(D, pymf_b200, args, "cfg2", steps, "pageable")
+            secondary["e2e_pageable"]["ratio_to_pinned"] = secondary["e2e_pageable"]["value"] / secondary["e2e"]["value"]
+        e2e = e2e_leg(D, pymf_b200, args, wl_name, steps, "pinned")
+        e2e_pageable = e2e_leg(D, pymf_b200, args, wl_name, steps, "pageable")
+        e2e_pageable["ratio_to_pinned"] = e2e_pageable["value"] / e2e["value"]
 
     cpu = None
     if D.rank == 0 and D.world == 1 and not args.no_cpu:

@@ -153,6 +153,21 @@ int pymfb_gen_x(pymfb_ctx* ctx, uint64_t seed);
  * place (numpy arrays are wrapped around them by pymf_b200.pinned_empty).
  */
 int pymfb_host_alloc(void** out, size_t bytes);
+/*
+ * Panel-streamed ingest - replaces the `data[:,:]` convention of pymf/nmf.py:110,125,131 (which exists so that
+ * `data` may be an h5py dataset, pymf/kmeans.py:71) for sources that are NOT host arrays: the host layer reads
+ * column panels data[:, c0:c1] into two page-locked panel buffers and hands each to upload_x_panel, so the host
+ * never holds more than two panels of X while the device copy is assembled.
+ *   upload_x_begin   make the context-owned X current (padding zeroed)
+ *   upload_x_panel   columns [col0, col0 + ncols) <- host panel (d x ncols, fp32 / fp64, leading dimension ld);
+ *                    asynchronous for page-locked panels: `slot` (0 / 1) names the panel buffer, and
+ *   upload_x_wait    blocks until the DMA that last read `slot` has finished (call before refilling the buffer)
+ *   upload_x_end     waits for everything and re-plans the kernels for the new data
+ */
+int pymfb_upload_x_begin(pymfb_ctx* ctx);
+int pymfb_upload_x_panel(pymfb_ctx* ctx, const void* panel_host, int dtype, int64_t ld, int64_t col0, int64_t ncols, int slot);
+int pymfb_upload_x_wait(pymfb_ctx* ctx, int slot);
+int pymfb_upload_x_end(pymfb_ctx* ctx);
 int pymfb_host_free(void* ptr);
 int pymfb_last_upload_pinned(pymfb_ctx* ctx);
 /* pymfb_host_alloc places the buffer on the NUMA node of the CURRENT device when the OS exposes one (mmap +
@@ -173,6 +188,17 @@ int pymfb_get_w(pymfb_ctx* ctx, void* w_host, int dtype);
 int pymfb_get_h(pymfb_ctx* ctx, void* h_host, int dtype);
 int pymfb_gen_w(pymfb_ctx* ctx, uint64_t seed);
 int pymfb_gen_h(pymfb_ctx* ctx, uint64_t seed);
+
+/*
+ * NNDSVD initialisation - replaces NNDSVD.update_w (pymf/nndsvd.py:79-108): W and H of the context are set to the
+ * non-negative double SVD start of Boutsidis & Gallopoulos, ready for pymfb_run (warm start) or pymfb_get_w/h.
+ * The leading k singular triplets of X come from subspace iteration (its two products per sweep are the
+ * contractions of the H-update and X H^T passes); the reference's second SVD of max(0, s_i u_i v_i^T) is taken
+ * in closed form.  max_iter <= 0 / tol <= 0 / extra_iter < 0 select the defaults (100 sweeps at most, Ritz values
+ * settled to 3e-7 relative, then 6 more sweeps).  sigma_out (k doubles, may be null) receives the singular
+ * values.  One rank only; k <= 200.
+ */
+int pymfb_nndsvd(pymfb_ctx* ctx, int max_iter, double tol, int extra_iter, int* iters_done, double* sigma_out);
 
 /*
  * Run `niter` iterations of the factorize() loop (pymf/nmf.py:182-202): per iteration

@@ -68,6 +68,27 @@ SNMF_CASES = {
 }
 
 
+# NNDSVD parity cases (pymf/nndsvd.py).  kind "lowrank": X = W* H* + 0.02 U with W*, H* >= 0 whose columns / rows are
+# scaled by a geometric sequence, so that the leading singular values are well separated (singular VECTORS are only
+# defined - and only comparable between an exact SVD and an iterative one - where the gaps are not tiny).
+NNDSVD_CASES = {
+    "nndsvd_small": dict(kind="lowrank", seed=41, d=60, n=90, k=4, rank=6),
+    "nndsvd_wide": dict(kind="lowrank", seed=43, d=300, n=2000, k=8, rank=12),
+    "nndsvd_tall": dict(kind="lowrank", seed=45, d=700, n=400, k=6, rank=10),       # rows > cols: the reference's _left_svd
+    "nndsvd_tc": dict(kind="lowrank", seed=47, d=1024, n=4096, k=16, rank=24),      # tensor-path shape of the NMF that follows
+}
+
+
+def build_nndsvd(name):
+    c = NNDSVD_CASES[name]
+    rng = np.random.RandomState(c["seed"])
+    d, n, r = c["d"], c["n"], c["rank"]
+    scale = 0.75 ** np.arange(r)
+    Ws = rng.random_sample((d, r)) * (rng.random_sample((d, r)) < 0.5) * scale[None, :]
+    Hs = rng.random_sample((r, n)) * (rng.random_sample((r, n)) < 0.5)
+    return Ws.dot(Hs) + 0.02 * rng.random_sample((d, n))
+
+
 def build(name):
     c = CASES[name] if name in CASES else (BNMF_CASES[name] if name in BNMF_CASES else SNMF_CASES[name])
     d, n, k = c["d"], c["n"], c["k"]

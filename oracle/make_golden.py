@@ -14,7 +14,7 @@ import sys
 import numpy as np
 
 from . import cases
-from .ref_loader import load_reference_bnmf, load_reference_nmf, load_reference_snmf
+from .ref_loader import load_reference_bnmf, load_reference_nmf, load_reference_nndsvd, load_reference_snmf
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -176,7 +176,33 @@ def main_snmf():
         print(name, "ferr", ferr[0], "->", ferr[-1])
 
 
+def main_nndsvd():
+    """NNDSVD fixtures from the unmodified pymf/nndsvd.py + pymf/svd.py: W, H, ferr of NNDSVD(X, k).factorize(), the
+    leading singular values, and the first 10 iterations of the reference NMF warm-started from them."""
+    refn = load_reference_nndsvd()
+    ref = load_reference_nmf()
+    if refn is None:
+        sys.exit("no reference checkout found (set PYMF_REF)")
+    import sys as _sys
+    svd_mod = _sys.modules["_pymf_ref_pkg.svd"]
+    for name, c in cases.NNDSVD_CASES.items():
+        X = cases.build_nndsvd(name)
+        m = refn.NNDSVD(X, num_bases=c["k"])
+        m.factorize()
+        sv = svd_mod.SVD(X)
+        sv.factorize()
+        f = ref.NMF(X, num_bases=c["k"])
+        f.W, f.H = m.W.copy(), m.H.copy()
+        f.factorize(niter=10)
+        np.savez(os.path.join(OUT, "%s.npz" % name), W=m.W, H=m.H, ferr=m.ferr, sigma=np.diag(sv.S)[:c["k"] + 4].copy(),
+                 W_nmf10=f.W, H_nmf10=f.H, ferr_nmf10=f.ferr)
+        print(name, "ferr", m.ferr, "sigma", np.diag(sv.S)[:c["k"] + 1], "nmf ferr", f.ferr[0], "->", f.ferr[-1])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nndsvd":
+        main_nndsvd()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "bnmf":
         main_bnmf()
         sys.exit(0)

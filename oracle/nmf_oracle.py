@@ -184,6 +184,58 @@ def snmf_factorize(X, W, H, niter=1, compute_w=True, compute_h=True, compute_err
 
 
 # --------------------------------------------------------------------------
+# NNDSVD (pymf/nndsvd.py) and the dense SVD it calls (pymf/svd.py).  Pinned by tests/golden/nndsvd_*.npz, which
+# come from the unmodified reference files.
+# --------------------------------------------------------------------------
+SVD_EPS = 10 ** -8            # pymf/svd.py:74
+
+
+def svd_dense(X):
+    """U, S (diagonal matrix), V with X = U S V.  pymf/svd.py:111-158,237-246: eigh of X X^T when rows <= cols
+    (_right_svd), of X^T X otherwise (_left_svd); eigenvalues <= 1e-8 are dropped, the rest sorted descending."""
+    rows, cols = X.shape
+    if rows > cols:                                              # _left_svd, :137-158
+        values, v_vectors = np.linalg.eigh(np.dot(X.T, X))       # :138-139
+        v_vectors = v_vectors[:, values > SVD_EPS]               # :142
+        values = values[values > SVD_EPS]                        # :143
+        idx = np.argsort(values)[::-1]                           # :147
+        values = values[idx]
+        S = np.diag(np.sqrt(values))                             # :151
+        S_inv = np.diag(1.0 / np.sqrt(values))                   # :154
+        Vtmp = v_vectors[:, idx]                                 # :156
+        U = np.dot(np.dot(X, Vtmp), S_inv)                       # :158
+        V = Vtmp.T
+    else:                                                        # _right_svd, :112-134
+        values, u_vectors = np.linalg.eigh(np.dot(X, X.T))       # :113-114
+        u_vectors = u_vectors[:, values > SVD_EPS]               # :117
+        values = values[values > SVD_EPS]                        # :118
+        idx = np.argsort(values)                                 # :121
+        values = values[idx[::-1]]                               # :122
+        U = u_vectors[:, idx[::-1]]                              # :125
+        S = np.diag(np.sqrt(values))                             # :128
+        S_inv = np.diag(np.sqrt(values) ** -1)                   # :131
+        V = np.dot(S_inv, np.dot(U.T, X))                        # :134
+    return U, S, V
+
+
+def nndsvd(X, k):
+    """W (d x k), H (k x n) of NNDSVD.update_w.  pymf/nndsvd.py:79-108 (init_w / init_h zeros, :70-74)."""
+    d, n = X.shape
+    W = np.zeros((d, k))
+    H = np.zeros((k, n))
+    U, S, V = svd_dense(X)                                       # :80-83
+    W[:, 0] = np.sqrt(S[0, 0]) * np.abs(U[:, 0])                 # :87
+    H[0, :] = np.sqrt(S[0, 0]) * np.abs(V[0, :].T)               # :90
+    for i in range(1, k):                                        # :92
+        Tmp = np.dot(U[:, i:i + 1] * S[i, i], V[i:i + 1, :])     # :94
+        Tmp = np.where(Tmp < 0, 0.0, Tmp)                        # :97
+        u, s, v = svd_dense(Tmp)                                 # :100-102
+        W[:, i] = np.sqrt(s[0, 0]) * np.abs(u[:, 0])             # :105
+        H[i, :] = np.sqrt(s[0, 0]) * np.abs(v[0, :].T)           # :108
+    return W, H
+
+
+# --------------------------------------------------------------------------
 # Synthetic inputs shared by tests, smoke() and bench.py (SURVEY.md section 8d).
 # The device generator in pymf_b200/csrc/pymfb.cu (k_gen_uniform) implements the
 # same integer hash so that any shard / tile regenerates bit-identically.

@@ -72,3 +72,9 @@ def load_reference_bnmf():
 
 def load_reference_snmf():
     return load_reference_submodule("snmf")
+
+
+def load_reference_nndsvd():
+    """pymf/nndsvd.py (and pymf/svd.py, which it imports) from the unmodified reference."""
+    load_reference_submodule("svd")
+    return load_reference_submodule("nndsvd")

@@ -47,6 +47,10 @@ SIGNATURES = {
     "pymfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pymfb_host_free": (C.c_int, [C.c_void_p]),
     "pymfb_last_upload_pinned": (C.c_int, [_c_ctx]),
+    "pymfb_upload_x_begin": (C.c_int, [_c_ctx]),
+    "pymfb_upload_x_panel": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, _i64, _i64, _i64, C.c_int]),
+    "pymfb_upload_x_wait": (C.c_int, [_c_ctx, C.c_int]),
+    "pymfb_upload_x_end": (C.c_int, [_c_ctx]),
     "pymfb_device_numa_node": (C.c_int, [C.c_int]),
     "pymfb_host_node_of": (C.c_int, [C.c_void_p]),
     "pymfb_set_w": (C.c_int, [_c_ctx, C.c_void_p, C.c_int]),
@@ -58,6 +62,7 @@ SIGNATURES = {
     "pymfb_run": (C.c_int, [_c_ctx, C.c_int, C.c_uint, C.POINTER(C.c_double),
                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pymfb_frobenius": (C.c_int, [_c_ctx, C.POINTER(C.c_double)]),
+    "pymfb_nndsvd": (C.c_int, [_c_ctx, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "pymfb_enqueue": (C.c_int, [_c_ctx, C.c_int, C.c_uint]),
     "pymfb_sync": (C.c_int, [_c_ctx]),
     "pymfb_stream": (C.c_void_p, [_c_ctx]),

@@ -11,6 +11,10 @@ constexpr double kEpsConv = 1e-8;    // pymf/nmf.py:69,136   (NMF._EPS)
 // Device-resident loop state.  The stop decision of factorize() (pymf/nmf.py:198-202)
 // is taken on the device so that the host never synchronises inside the loop: once
 // `stop` is set every later kernel of the run returns immediately.
+// xx - 2<W,A> + <G,B> carries an absolute error of ~2e-7 ||X||^2 (fp32 A, B and their accumulation), i.e. a relative
+// error of ~2e-7 ||X||^2 / e^2 in ferr^2.  Below this ratio (ferr off by > ~1e-4) the identity is no longer trusted.
+constexpr double kTraceCancel = 1e-3;
+
 struct DevState {
     int stop;            // 1 after converged(i) fired
     int n_exec;          // iterations executed when stop fired (i + 1)
@@ -22,6 +26,8 @@ struct DevState {
     double resid_local;  // direct-residual mode: this rank's sum (X - W H)^2
     double resid;        // ... summed over ranks
     unsigned ticket3;    // last-block-done counter of the direct residual
+    int cancel;          // trace-identity error below kTraceCancel * ||X||^2 seen: the identity has lost too many digits
+                         // (the host switches this context to the direct residual pass for its next calls)
     int it;              // iteration index inside the current run: k_err stores ferr[it] and advances it, so the
                          // per-iteration launch sequence carries no host-side index (replayable as a CUDA graph)
 };

@@ -266,10 +266,16 @@ template <int KB>
 __global__ void __launch_bounds__(SIMT_THREADS)
 k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t rows,
            const float* __restrict__ H, int64_t ldh, int64_t n_loc, int64_t cols_per_split,
-           float* __restrict__ P, int64_t ldp, int nrb_x, int64_t rows_h, float* __restrict__ PB) {
+           float* __restrict__ P, int64_t ldp, int nrb_x, int64_t rows_h, float* __restrict__ PB,
+           float* __restrict__ Ppart, int64_t part_stride, unsigned* __restrict__ tickets) {
     // Row blocks [0, nrb_x) of the grid compute X H^T; when PB != nullptr the remaining row blocks compute H H^T in
     // the same launch (the streamed operand is then H itself, rows_h rows, output PB) - one launch instead of two.
+    // Column splits (gridDim.y) are combined DETERMINISTICALLY when Ppart != nullptr: every split parks its block in
+    // copy blockIdx.y of the [A | B] layout (part_stride floats apart), and the split that arrives last on the
+    // block's ticket sums the copies in split order and overwrites P (no clearing, no atomics: W is bit-reproducible
+    // from run to run).  Ppart == nullptr: fp32 atomics into a cleared P.
     if (st->stop) return;
+    const int64_t out_off = ((int)blockIdx.x >= nrb_x) ? (PB - P) : 0;
     if ((int)blockIdx.x >= nrb_x) { X = H; ldx = ldh; rows = rows_h; P = PB; }
     constexpr int TK = KB / 8;
     __shared__ float Xs[128][XHT_CK + 1];
@@ -333,12 +339,61 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
         }
         __syncthreads();
     }
+    if (Ppart == nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = row0 + tr + 32 * i;
+            if (r < rows) {
+#pragma unroll
+                for (int j = 0; j < TK; ++j) atomicAdd(P + r * ldp + kb0 + tk * TK + j, acc[i][j]);
+            }
+        }
+        return;
+    }
+    const int ns = (int)gridDim.y;
+    if (ns > 1) {
+        float* part = Ppart + (int64_t)blockIdx.y * part_stride + out_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = row0 + tr + 32 * i;
+            if (r < rows) {
+#pragma unroll
+                for (int j = 0; j < TK; ++j) part[r * ldp + kb0 + tk * TK + j] = acc[i][j];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        __shared__ bool last;
+        if (tid == 0) {
+            unsigned* tk_ = tickets + (int64_t)blockIdx.x * gridDim.z + blockIdx.z;
+            last = atomicAdd(tk_, 1u) == (unsigned)(ns - 1);
+            if (last) *tk_ = 0u;                   // ready for the next launch
+        }
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TK; ++j) acc[i][j] = 0.f;
+        for (int sp = 0; sp < ns; ++sp) {
+            const float* part_s = Ppart + (int64_t)sp * part_stride + out_off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = row0 + tr + 32 * i;
+                if (r < rows) {
+#pragma unroll
+                    for (int j = 0; j < TK; ++j) acc[i][j] += __ldcg(part_s + r * ldp + kb0 + tk * TK + j);
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t r = row0 + tr + 32 * i;
         if (r < rows) {
 #pragma unroll
-            for (int j = 0; j < TK; ++j) atomicAdd(P + r * ldp + kb0 + tk * TK + j, acc[i][j]);
+            for (int j = 0; j < TK; ++j) P[r * ldp + kb0 + tk * TK + j] = acc[i][j];
         }
     }
 }
@@ -537,6 +592,10 @@ k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __res
             tgb += ((volatile double*)scratch)[ERR_BLOCKS + b];
         }
         double e2 = direct ? st->resid : st->xx - 2.0 * twa + tgb;
+        // near-exact fit: the identity cancels (see kTraceCancel).  Flag it for the host and take no convergence
+        // decision from a value that is mostly rounding noise.
+        const bool cancelled = !direct && e2 < kTraceCancel * st->xx;
+        if (cancelled) st->cancel = 1;
         double e = sqrt(e2 > 0.0 ? e2 : 0.0);
         st->last_ferr = e;
         st->ticket = 0;
@@ -544,7 +603,7 @@ k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __res
             const int iter = st->it;       // device-side iteration counter (reset by the host at the start of a run)
             st->it = iter + 1;
             ferr[iter] = e;
-            if (early_stop && iter > 1) {
+            if (early_stop && iter > 1 && !cancelled) {
                 double derr = fabs(e - ferr[iter - 1]) / n_samples;
                 if (derr < kEpsConv) { st->stop = 1; st->n_exec = iter + 1; }
             }

@@ -94,6 +94,7 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -475,8 +476,12 @@ template <int KP>
 __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
-         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp) {
+         int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp,
+         float* __restrict__ Ppart, int64_t part_stride) {
     // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
+    // Ppart != nullptr: deterministic combine of the column splits - every task stores its sums in copy (task / num_rb)
+    // of P's layout (part_stride floats apart) and k_sum_copies adds the copies in split order into P afterwards.
+    // Ppart == nullptr: fp32 atomics into a cleared P.
     using Cfg = XCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -634,9 +639,15 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 for (int j = 0; j < Cfg::NJ; ++j) o[j] = areg[j];
             }
             if (row < d) {
-                float* dst = P + (int64_t)row * ldp + jbase;
+                if (Ppart == nullptr) {
+                    float* dst = P + (int64_t)row * ldp + jbase;
 #pragma unroll
-                for (int j = 0; j < Cfg::NJ; ++j) atomicAdd(dst + j, areg[j]);
+                    for (int j = 0; j < Cfg::NJ; ++j) atomicAdd(dst + j, areg[j]);
+                } else {                               // this split's copy of P; k_sum_copies adds the copies in order
+                    float* dst = Ppart + (int64_t)(task / num_rb) * part_stride + (int64_t)row * ldp + jbase;
+#pragma unroll
+                    for (int j = 0; j < Cfg::NJ; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(areg[j], areg[j + 1], areg[j + 2], areg[j + 3]);
+                }
             }
         }
     }
@@ -758,6 +769,9 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
     // as H, written by k_gh_posneg_simt) instead of the G H accumulator
+    __shared__ float s_mean[2 * KP];          // [w_mean | g_mean]: read on the critical tail of every tile, so not from global
+    if (threadIdx.x < 2 * KP)
+        s_mean[threadIdx.x] = (wmean == nullptr) ? 0.f : (threadIdx.x < KP ? wmean[threadIdx.x] : gmean[threadIdx.x - KP]);
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -997,8 +1011,8 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                             const float h = hreg[j0 + j];
                             float cj = creg[j0 + j], dj = dh[j] + dl[j];
                             if (wmean != nullptr) {
-                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
-                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+                                cj = fmaf(s_mean[j0 + j], xs, cj);
+                                dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
                             }
                             const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
@@ -1034,7 +1048,9 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
          const __grid_constant__ CUtensorMap mapHA, const DevState* __restrict__ st,
          float* __restrict__ PA, float* __restrict__ PB, int d, int n_loc,
          int cols_per_task, int num_rb, int x_tasks, int hh_cols_per_task, int num_tasks,
-         float* __restrict__ dbg) {
+         float* __restrict__ dbg, float* __restrict__ PpartA, float* __restrict__ PpartB) {
+    // PpartA != nullptr: deterministic combine of the column splits (see k_xht_tc): copies of A are d * KP floats
+    // apart, copies of B = H H^T (one per H H^T task) KP * KP floats; k_sum_copies then writes P.
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -1213,15 +1229,45 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 for (int j = 0; j < KP; ++j) o[j] = areg[j];
             }
             if (row < (hh ? KP : d)) {
-                float* dst = (hh ? PB : PA) + (int64_t)row * KP;
+                if (PpartA == nullptr) {
+                    float* dst = (hh ? PB : PA) + (int64_t)row * KP;
 #pragma unroll
-                for (int j = 0; j < KP; ++j) atomicAdd(dst + j, areg[j]);
+                    for (int j = 0; j < KP; ++j) atomicAdd(dst + j, areg[j]);
+                } else {
+                    float* dst = hh ? PpartB + ((int64_t)(task - x_tasks) * KP + row) * KP
+                                    : PpartA + ((int64_t)(task / num_rb) * d + row) * KP;
+#pragma unroll
+                    for (int j = 0; j < KP; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(areg[j], areg[j + 1], areg[j + 2], areg[j + 3]);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == NPROD) tmem_dealloc(tmem_base, 512);
+}
+
+// outA[i] = sum over the copies of A (in copy order: fixed summation order, bit-reproducible), then the same for B;
+// ONE launch for both regions.  Counts are multiples of 4 (kp % 32 == 0).
+__global__ void __launch_bounds__(256)
+k_sum_copies(const DevState* __restrict__ st, const float* __restrict__ copiesA, int ncopiesA, int64_t countA,
+             float* __restrict__ outA, const float* __restrict__ copiesB, int ncopiesB, int64_t countB,
+             float* __restrict__ outB) {
+    if (st->stop) return;
+    const int64_t nA4 = countA >> 2, nB4 = countB >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nA4 + nB4; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool isb = i >= nA4;
+        const int64_t e = isb ? i - nA4 : i, count = isb ? countB : countA;
+        const float* src = isb ? copiesB : copiesA;
+        const int nc = isb ? ncopiesB : ncopiesA;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)c * count) + e);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(isb ? outB : outA)[e] = a;
+    }
 }
 
 // Rows [row0, row0 + kpb) of H (.. x ldh) -> chunk-major Hs = [H_hi rows ; H_lo rows] of that block; used when
@@ -1353,6 +1399,9 @@ struct TcPlan {
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
     const float* Dp = nullptr; // Semi-NMF: G+ H and G- H of the H buffer being updated (set by the scheduler), else null
     const float* Dn = nullptr;
+    float* xpart = nullptr;    // deterministic combine of the X H^T / H H^T column splits: x_splits copies of A, then
+    float* xpartB = nullptr;   //   hh_tasks copies of B (null: fp32 atomics)
+    int x_splits = 0;
     bool center = false;       // TS kernels: contract against the centered W / G (see "centering" above)
     float* xsum = nullptr;     // n_loc column sums of X (center)
     bool xsum_valid = false;
@@ -1465,6 +1514,8 @@ inline void tc_release(TcPlan& p) {
 #endif
     if (p.Wsplit) cudaFree(p.Wsplit);
     if (p.Gsplit) cudaFree(p.Gsplit);
+    if (p.xpart) cudaFree(p.xpart);
+    p.xpart = p.xpartB = nullptr;
     if (p.xsum) cudaFree(p.xsum);
     if (p.wmean) cudaFree(p.wmean);
     p.xsum = p.wmean = p.gmean = p.cm_part = nullptr; p.xsum_valid = false; p.center = false;
@@ -1570,6 +1621,17 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         p.hh_cols_per_task = (int)(hper * 32);
         p.hh_tasks = (int)((chunks + hper - 1) / hper);
     }
+    {   // Deterministic combine (bit-reproducible W): partial copies instead of atomics while they stay below 1 GiB
+        // (cfg3 on ONE GPU would need 259 x 8 MiB and keeps the atomics; PYMFB_DETERMINISTIC=1 forces, =0 disables)
+        p.x_splits = p.x_tasks / p.x_rb;
+        const size_t bytes = ((size_t)p.x_splits * d * kp + (size_t)p.hh_tasks * kp * kp) * sizeof(float);
+        const char* e = getenv("PYMFB_DETERMINISTIC");
+        const bool want = e ? e[0] == '1' : bytes <= ((size_t)1 << 30);
+        if (want) {
+            if (cudaMalloc(&p.xpart, bytes) != cudaSuccess) { p.err = "cudaMalloc X.H^T partial copies failed"; return 1; }
+            p.xpartB = p.xpart + (size_t)p.x_splits * d * kp;
+        }
+    }
     p.ready = true;
     return 0;
 }
@@ -1629,7 +1691,7 @@ inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     const int grid = std::min(ntasks, p.sm_count);
     tc::k_xht_ts<KP><<<grid, tc::X_THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_x, p.mapH_x[hsrc], p.mapH_a[hsrc], st, P, P + p.d * p.kp, (int)p.d, (int)p.n_loc, p.x_cols_per_task,
-        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg);
+        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg, p.xpart, p.xpartB);
 }
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
@@ -1655,7 +1717,7 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
-            p.dbg, p.kp);
+            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp);
 }
 // true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
 // extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
@@ -1669,7 +1731,7 @@ inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cu
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
-            nullptr, p.kp);
+            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
@@ -1680,9 +1742,17 @@ inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cuda
         *launches += p.nblk;
         p.hs_valid[hsrc] = true;
     }
+    auto sum_copies = [&]() {      // deterministic combine: P = sum of the splits' copies, in split order
+        if (!p.xpart) return;
+        const int64_t na = p.d * p.kp, nb = (int64_t)p.kp * p.kp;
+        tc::k_sum_copies<<<(unsigned)std::min<int64_t>(((na + nb) / 4 + 255) / 256, 8 * p.sm_count), 256, 0, stream>>>(
+            st, p.xpart, p.x_splits, na, P, p.xpartB, p.hh_tasks, nb, P + na);
+        *launches += 1;
+    };
     if (p.use_ts) {
         if (p.kp == 32) ts_launch_x<32>(p, st, hsrc, P, stream); else ts_launch_x<64>(p, st, hsrc, P, stream);
         *launches += 1;
+        sum_copies();
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
     switch (p.kpb) {
@@ -1699,6 +1769,7 @@ inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cuda
         default: tc_launch_hht<128>(p, st, hsrc, PB, stream); break;
     }
     *launches += 2 * p.nblk;
+    sum_copies();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

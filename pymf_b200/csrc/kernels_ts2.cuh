@@ -96,6 +96,9 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
     // as H, written by k_gh_posneg_simt) instead of the G H accumulator
+    __shared__ float s_mean[2 * KP];          // [w_mean | g_mean]: read on the critical tail of every tile, so not from global
+    if (threadIdx.x < 2 * KP)
+        s_mean[threadIdx.x] = (wmean == nullptr) ? 0.f : (threadIdx.x < KP ? wmean[threadIdx.x] : gmean[threadIdx.x - KP]);
     using Cfg = Ts2Cfg<KP>;
     if (st->stop) return;
     uint32_t rank;
@@ -335,8 +338,8 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                             const float h = hreg[j0 + j];
                             float cj = creg[j0 + j], dj = dh[j] + dl[j];
                             if (wmean != nullptr) {
-                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
-                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+                                cj = fmaf(s_mean[j0 + j], xs, cj);
+                                dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
                             }
                             const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);

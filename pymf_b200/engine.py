@@ -53,6 +53,15 @@ def pinned_empty(shape, dtype=np.float32):
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
+def panel_ranges(d, n, itemsize, panel_bytes=64 << 20):
+    """Column panels (first column, width) of a d x n source for the panel-streamed ingest: about panel_bytes each,
+    widths a multiple of 128 columns (except the last), at least 128."""
+    pw = int(panel_bytes) // (int(d) * int(itemsize))
+    pw = n if pw >= n else max(128, pw // 128 * 128)
+    pw = max(1, min(pw, n))
+    return pw, [(c0, min(pw, n - c0)) for c0 in range(0, n, pw)]
+
+
 def numa_info(array=None, device=0):
     """(NUMA node of the GPU, NUMA node holding the first page of `array`), -1 where unknown."""
     lib = _lib.load()
@@ -161,6 +170,31 @@ class Engine(object):
         ld = x.strides[0] // x.itemsize
         _lib.check(self._lib.pymfb_upload_x(self._ctx, x.ctypes.data_as(C.c_void_p), _dtype_code(x), ld))
 
+    def upload_x_panels(self, source, panel_bytes=64 << 20):
+        """Assemble the device copy of X from column panels ``source[:, c0:c1]`` of an h5py-like object (anything
+        with ``.shape`` and 2-D slicing that is not a host array).  Two page-locked panel buffers alternate: one is
+        being filled from the source while the copy engine reads the other, so the host never holds more than two
+        panels (plus whatever temporary the source's own ``__getitem__`` returns).  Returns the panel width."""
+        d, n = self.d, self.n_local
+        if tuple(source.shape) != (d, n):
+            raise ValueError("data shape %r != (%d, %d)" % (tuple(source.shape), d, n))
+        dt = np.dtype(getattr(source, "dtype", np.float64))
+        dt = np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
+        pw, ranges = panel_ranges(d, n, dt.itemsize, panel_bytes)
+        bufs = [pinned_empty((d, pw), dt), pinned_empty((d, pw), dt)]
+        _lib.check(self._lib.pymfb_upload_x_begin(self._ctx))
+        for i, (c0, w) in enumerate(ranges):
+            slot = i & 1
+            _lib.check(self._lib.pymfb_upload_x_wait(self._ctx, slot))          # the DMA that last read this buffer
+            view = bufs[slot][:, :w]
+            if w == pw and hasattr(source, "read_direct"):                      # h5py: straight into the pinned buffer
+                source.read_direct(bufs[slot], np.s_[:, c0:c0 + w])
+            else:
+                view[...] = source[:, c0:c0 + w]
+            _lib.check(self._lib.pymfb_upload_x_panel(self._ctx, view.ctypes.data_as(C.c_void_p), _dtype_code(view), pw, c0, w, slot))
+        _lib.check(self._lib.pymfb_upload_x_end(self._ctx))
+        return pw
+
     @property
     def last_upload_pinned(self):
         """True if the last upload_x read page-locked memory by direct DMA."""
@@ -226,6 +260,14 @@ class Engine(object):
                                        ferr.ctypes.data_as(C.POINTER(C.c_double)),
                                        C.byref(done), C.byref(nf)))
         return ferr[:nf.value].copy(), done.value
+
+    def nndsvd(self, max_iter=0, tol=0.0, extra_iter=-1):
+        """Set the device W / H to the NNDSVD start (pymf/nndsvd.py:79-108).  Returns (singular values, sweeps)."""
+        sig = np.zeros(self.k, dtype=np.float64)
+        it = C.c_int(0)
+        _lib.check(self._lib.pymfb_nndsvd(self._ctx, int(max_iter), float(tol), int(extra_iter), C.byref(it),
+                                          sig.ctypes.data_as(C.POINTER(C.c_double))))
+        return sig, it.value
 
     def frobenius(self):
         out = C.c_double(0.0)

@@ -224,7 +224,12 @@ class NMF(object):
                     return
                 x = x.numpy()
         if not isinstance(x, np.ndarray):
-            x = np.asarray(x[:, :])                  # h5py-style sources, pymf/nmf.py:110,125,131
+            if hasattr(x, "shape") and hasattr(x, "__getitem__") and len(getattr(x, "shape", ())) == 2:
+                # h5py-style sources (the reason for the reference's `data[:,:]`, pymf/nmf.py:110,125,131): read
+                # column panels data[:, c0:c1], never the whole matrix, straight into the device copy
+                self._engine.upload_x_panels(x)
+                return
+            x = np.asarray(x)                        # lists / array-likes
         self._engine.upload_x(x)
 
     def _sync_to_device(self):

@@ -53,6 +53,16 @@ class FakeEngine(object):
         self.X = np.array(x, dtype=np.float64)
         self.uploads["x"] += 1
 
+    def upload_x_panels(self, source, panel_bytes=64 << 20):
+        from pymf_b200.engine import panel_ranges
+        dt = np.dtype(getattr(source, "dtype", np.float64))
+        pw, ranges = panel_ranges(self.d, self.n_local, 4 if dt == np.float32 else 8, panel_bytes)
+        self.X = np.empty((self.d, self.n_local))
+        for c0, w in ranges:
+            self.X[:, c0:c0 + w] = source[:, c0:c0 + w]
+        self.uploads["x"] += 1
+        return pw
+
     def set_w(self, w):
         self.W = np.array(w, dtype=np.float64)
         self.uploads["w"] += 1

@@ -73,3 +73,61 @@ def test_two_gpus_match_oracle(tmp_path, shape, path, cls):
         assert np.max(np.abs(p["ferr"] - ferr) / ferr) < 1e-3
     np.testing.assert_array_equal(parts[0]["W"], parts[1]["W"])      # replicas stay bit-identical
     np.testing.assert_array_equal(parts[0]["ferr"], parts[1]["ferr"])
+
+
+WORKER_GRAPH = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import pymf_b200
+from oracle import nmf_oracle as O
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+d, n, k, niter = 1000, 500, 10, 31
+X = O.gen_matrix(21, d, n)
+lo, hi = (0, 250) if rank == 0 else (250, 500)
+np.random.seed(100 + rank)                      # every rank on its OWN random stream: W must still be one replica
+res = []
+for rep in range(2):
+    m = pymf_b200.NMF(np.ascontiguousarray(X[:, lo:hi]), num_bases=k, process_group=True, device=rank)
+    m.W = O.gen_matrix(22 + rank, d, k).astype(np.float64)     # rank 1 assigns a DIFFERENT W: rank 0's wins
+    m.H = O.gen_matrix(23, k, n).astype(np.float64)[:, lo:hi].copy()
+    m.factorize(niter=niter)
+    res.append((m.W.copy(), m.H.copy(), m.ferr.copy(), m._engine.graph_replays))
+np.savez(os.path.join(%(out)r, "g%%d.npz" %% rank), W=res[0][0], H=res[0][1], ferr=res[0][2], W2=res[1][0], H2=res[1][1],
+         replays=res[0][3], lo=lo, hi=hi)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_small_problem_replays_graphs_and_is_reproducible(tmp_path):
+    """cfg1-sized problem on 2 ranks: the iteration body INCLUDING the in-place ncclAllReduce replays as a CUDA graph
+    (graph_replays > 0), two runs in the same process give bit-identical W / H (deterministic split combine), the
+    replicas agree bit for bit although rank 1 assigned a different W (rank 0's is broadcast), and the result
+    matches the oracle started from rank 0's W."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker_graph.py"
+    script.write_text(WORKER_GRAPH % dict(root=ROOT, out=str(tmp_path)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    from oracle import nmf_oracle as O
+    p0, p1 = [np.load(str(tmp_path / ("g%d.npz" % r_))) for r_ in range(2)]
+    assert int(p0["replays"]) > 0 and int(p1["replays"]) > 0
+    np.testing.assert_array_equal(p0["W"], p1["W"])
+    np.testing.assert_array_equal(p0["ferr"], p1["ferr"])
+    for p in (p0, p1):
+        np.testing.assert_array_equal(p["W"], p["W2"])
+        np.testing.assert_array_equal(p["H"], p["H2"])
+    X = O.gen_matrix(21, 1000, 500).astype(np.float64)
+    W = O.gen_matrix(22, 1000, 10).astype(np.float64)
+    H = O.gen_matrix(23, 10, 500).astype(np.float64)
+    ferr = O.factorize(X, W, H, niter=31)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(p0["W"], W) < 1e-4
+    assert rel(np.concatenate([p0["H"], p1["H"]], axis=1), H) < 1e-4
+    assert np.max(np.abs(p0["ferr"] - ferr[:len(p0["ferr"])]) / ferr[:len(p0["ferr"])]) < 1e-3

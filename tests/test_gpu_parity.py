@@ -516,3 +516,85 @@ def test_cta_pair_h_update_kernel_is_bit_identical(shape, monkeypatch):
             e.close()
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,path", [((1000, 500, 10), "simt"), ((512, 4096, 32), "tc"), ((1024, 4096, 128), "tc"),
+                                        ((300, 3000, 40), "tc")])
+def test_runs_are_bit_reproducible(shape, path):
+    """The column splits of X H^T / H H^T are combined in a fixed order (partial copies + ticket, no atomics), so
+    two runs of the same problem in one process give bit-identical W, H and ferr."""
+    d, n, k = shape
+    X = O.gen_matrix(71, d, n)
+    W0 = O.gen_matrix(72, d, k).astype(np.float64)
+    H0 = O.gen_matrix(73, k, n).astype(np.float64)
+    out = []
+    for _ in range(2):
+        e = pymf_b200.Engine(d, n, k, path=path)
+        try:
+            e.upload_x(X); e.set_w(W0); e.set_h(H0)
+            f, done = e.run(9, early_stop=False)
+            out.append((e.get_w(np.float32), e.get_h(np.float32), f))
+        finally:
+            e.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=9, early_stop=False)
+    assert rel(out[0][0], Wr) < TOL_WH and rel(out[0][1], Hr) < TOL_WH
+    assert np.max(np.abs(out[0][2] - fr) / fr) < TOL_FERR
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_panel_streamed_ingest_equals_in_memory_ingest(dtype, monkeypatch):
+    """An h5py-like source (only `.shape`, `.dtype`, slicing) is ingested in column panels data[:, c0:c1] through two
+    page-locked panel buffers (pymfb_upload_x_panel); the device matrix, hence the trajectory, is the one of the
+    in-memory upload - ragged last panel, fp64 panels cast on the device."""
+    import pymf_b200.engine as eng_mod
+    from tests.test_host_logic import RecordingSource
+    d, n, k = 300, 5000, 8
+    rng = np.random.RandomState(8)
+    X = rng.random_sample((d, n)).astype(dtype)
+    W0 = rng.random_sample((d, k)); H0 = rng.random_sample((k, n))
+    orig = eng_mod.panel_ranges
+    monkeypatch.setattr(eng_mod, "panel_ranges", lambda d_, n_, isz, pb=0: orig(d_, n_, isz, d * isz * 640))
+    src = RecordingSource(X)
+    out = []
+    for data in (src, X):
+        m = pymf_b200.NMF(data, num_bases=k)
+        m.W, m.H = W0.copy(), H0.copy()
+        m.factorize(niter=1, compute_w=False, compute_err=False)      # one H update: no split combine, bit-exact
+        h1 = m.H.copy()
+        m.W, m.H = W0.copy(), H0.copy()
+        m.factorize(niter=4)
+        out.append((h1, m.W.copy(), m.H.copy(), m.ferr.copy()))
+    assert len(src.reads) == 8 and src.widest_read() == 640            # 7 x 640 + 520 columns
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=4)
+    assert rel(out[0][1], Wr) < TOL_WH and rel(out[0][2], Hr) < TOL_WH
+    assert np.max(np.abs(out[0][3] - fr) / fr) < TOL_FERR
+
+
+def test_trace_identity_hands_over_to_the_direct_residual_when_it_cancels():
+    """Near-exact low-rank data at a size where the error normally comes from the trace identity (d n k > 2^28):
+    once ferr^2 drops below 1e-3 ||X||^2 the identity has lost its digits; the library flags it, takes no early-stop
+    decision from such a value, and measures the error directly (pymf/nmf.py:110 as written) from the next call on."""
+    d, n, k, r = 2048, 8192, 32, 4
+    rng = np.random.RandomState(1)
+    X = (rng.random_sample((d, r)).dot(rng.random_sample((r, n))) + 1e-4 * rng.random_sample((d, n))).astype(np.float32)
+    W0 = rng.random_sample((d, k)); H0 = rng.random_sample((k, n))
+    m = pymf_b200.NMF(X, num_bases=k)
+    m.W, m.H = W0.copy(), H0.copy()
+    m.factorize(niter=150)
+    xx = float(np.sum(X.astype(np.float64) ** 2))
+    assert m.ferr[-1] ** 2 < 1e-3 * xx                        # deep in the cancelling regime
+    assert len(m.ferr) == 150                                   # no noise-driven early stop
+    W, H = m.W.copy(), m.H.copy()
+    true = O.frobenius_norm(X.astype(np.float64), W, H)
+    assert abs(m.frobenius_norm() - true) / true < TOL_FERR    # measured directly now
+    m.factorize(niter=3)
+    Wr, Hr = W.copy(), H.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=3)
+    assert np.max(np.abs(m.ferr - fr) / fr) < TOL_FERR

@@ -157,24 +157,38 @@ def test_progress_logging(NMF, caplog):
     assert logging.getLogger("pymf").level == logging.ERROR
 
 
-def test_h5py_style_data_source_is_read_through_full_slice(NMF):
-    """The reference only ever touches `data` through `data[:,:]` and `.shape` (pymf/nmf.py:97,110,125,131 -
-    the h5py convention of the package, pymf/kmeans.py:71); any object offering those two works here too."""
-    reads = []
+class RecordingSource(object):
+    """h5py-like stand-in: `.shape`, `.dtype` and 2-D slicing only; records every slice requested."""
 
-    class Sliceable(object):
-        def __init__(self, a):
-            self._a = a
-            self.shape = a.shape
+    def __init__(self, a):
+        self._a = a
+        self.shape = a.shape
+        self.dtype = a.dtype
+        self.reads = []
 
-        def __getitem__(self, key):
-            reads.append(key)
-            return self._a[key]
+    def __getitem__(self, key):
+        self.reads.append(key)
+        return self._a[key]
 
+    def widest_read(self):
+        n = self.shape[1]
+        return max(len(range(*k[1].indices(n))) for k in self.reads)
+
+
+def test_h5py_style_data_source_is_read_in_column_panels(NMF, monkeypatch):
+    """The reference touches `data` only through `data[:,:]` and `.shape` (pymf/nmf.py:97,110,125,131 - the h5py
+    convention of the package, pymf/kmeans.py:71) and pulls the whole matrix into RAM on every call.  Here any object
+    offering `.shape` and slicing is read ONCE, in column panels data[:, c0:c1] of bounded size, never as a whole."""
+    import pymf_b200.engine as eng_mod
     rng = np.random.RandomState(3)
-    X = rng.random_sample((9, 20))
-    W0, H0 = rng.random_sample((9, 3)), rng.random_sample((3, 20))
-    a = NMF(Sliceable(X), num_bases=3)
+    d, n = 9, 1000
+    X = rng.random_sample((d, n))
+    W0, H0 = rng.random_sample((d, 3)), rng.random_sample((3, n))
+    # 128-column panels: 9 rows x 8 bytes x 128 columns
+    orig = eng_mod.panel_ranges
+    monkeypatch.setattr(eng_mod, "panel_ranges", lambda d_, n_, isz, pb=0: orig(d_, n_, isz, 9 * 8 * 128))
+    src = RecordingSource(X)
+    a = NMF(src, num_bases=3)
     a.W, a.H = W0.copy(), H0.copy()
     a.factorize(niter=4)
     b = NMF(X, num_bases=3)
@@ -182,6 +196,19 @@ def test_h5py_style_data_source_is_read_through_full_slice(NMF):
     b.factorize(niter=4)
     np.testing.assert_array_equal(a.ferr, b.ferr)
     np.testing.assert_array_equal(a.W, b.W)
-    assert len(reads) == 1 and reads[0] == (slice(None), slice(None))     # read once, then resident
+    assert len(src.reads) == 8 and src.widest_read() == 128           # 7 x 128 + 104 columns, no full-matrix read
+    assert all(k[0] == slice(None) for k in src.reads)
+    cols = sorted((k[1].start, k[1].stop) for k in src.reads)
+    assert cols[0][0] == 0 and cols[-1][1] == n and all(cols[i][1] == cols[i + 1][0] for i in range(len(cols) - 1))
     a.factorize(niter=2)
-    assert len(reads) == 1
+    assert len(src.reads) == 8                                        # resident: not read again
+
+
+def test_panel_ranges_cover_the_matrix():
+    from pymf_b200.engine import panel_ranges
+    pw, r = panel_ranges(16384, 1 << 20, 4)                           # cfg3: 64 MiB panels of 1024 columns
+    assert pw == 1024 and len(r) == 1024 and r[0] == (0, 1024) and r[-1] == ((1 << 20) - 1024, 1024)
+    pw, r = panel_ranges(3, 50, 8)
+    assert pw == 50 and r == [(0, 50)]
+    pw, r = panel_ranges(1000, 300, 8, 1000 * 8 * 130)
+    assert pw == 128 and r == [(0, 128), (128, 128), (256, 44)]
