@@ -553,7 +553,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 block of the default (cfg3) line")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--shape", default=None, help="experiment: d,n,k of an ad-hoc weak-scaled workload (overrides --workload)")
     args = ap.parse_args()
+    if args.shape:
+        d_, n_, k_ = (int(v) for v in args.shape.split(","))
+        WORKLOADS["custom"] = (d_, n_, k_, "weak", "custom: %dx%d, k=%d" % (d_, n_, k_))
+        args.workload = "custom"
     if args.impl == "reference":
         run_reference(args, args.workload)
     else:

@@ -11,6 +11,17 @@ constexpr double kEpsConv = 1e-8;    // pymf/nmf.py:69,136   (NMF._EPS)
 // Device-resident loop state.  The stop decision of factorize() (pymf/nmf.py:198-202)
 // is taken on the device so that the host never synchronises inside the loop: once
 // `stop` is set every later kernel of the run returns immediately.
+// Layout of the data matrix X.  Row-major (leading dimension ldx) for borrowed matrices and small ones; context-owned
+// copies of wide matrices are PANEL-MAJOR: column panels of 2^xsh columns, each a dense d x 2^xsh block (row stride
+// ldx = 2^xsh), xps floats apart.  A TMA box of 128 rows then spans 128 x 16 KB = one 2 MB page instead of 128 pages
+// (row stride 4 MB at n = 2^20): the X H^T pass of cfg3 ran 12 % faster at a quarter of the stride.
+// Element (r, c) lives at X + xpanel_off(c, xps, xsh) + r * ldx + c;  row-major is xps = 0, xsh = kNoPanelShift.
+constexpr int kNoPanelShift = 40;
+__host__ __device__ __forceinline__ int64_t xpanel_off(int64_t col, int64_t xps, int xsh) {
+    const int64_t p = col >> xsh;
+    return p * xps - (p << xsh);
+}
+
 // xx - 2<W,A> + <G,B> carries an absolute error of ~2e-7 ||X||^2 (fp32 A, B and their accumulation), i.e. a relative
 // error of ~2e-7 ||X||^2 / e^2 in ferr^2.  Below this ratio (ferr off by > ~1e-4) the identity is no longer trusted.
 constexpr double kTraceCancel = 1e-3;

@@ -71,6 +71,7 @@ struct FusedParams {
     int64_t ldh;
     int d, n_loc, n_tiles;
     int nslab, ngroups, depth, nslot, hint;
+    int xsh;                // log2 of the panel width of X (tma_load_x)
     int pf;                 // L2 prefetch distance of the A tasks in tiles of this group (0 = off)
     const float* wmean;     // centered W (kernels_tc.cuh "centering"): column means of W and column sums of X, else null
     const float* xsum;
@@ -182,6 +183,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ void tma_load_x_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, int xsh, uint64_t policy) {
+    const int pn = col >> xsh;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(col - (pn << xsh)), "r"(row), "r"(pn), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_x_hint(const CUtensorMap* map, int col, int row, int xsh, uint64_t policy) {
+    const int pn = col >> xsh;
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.L2::cache_hint [%0, {%1, %2, %3}], %4;" ::"l"(map), "r"(col - (pn << xsh)), "r"(row), "r"(pn), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d_hint(const CUtensorMap* map, int c0, int c1, uint64_t policy) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.L2::cache_hint [%0, {%1, %2}], %3;" ::"l"(map), "r"(c0), "r"(c1), "l"(policy) : "memory");
@@ -335,9 +346,9 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                     if (t.type == 0) {
                         const int r0 = row_slab + it * R1;
                         if (p.pf && t.tile + p.pf * p.ngroups < p.n_tiles)     // the same rows of the A task `pf` tiles ahead -> L2
-                            tma_prefetch_2d_hint(&mapXp, (t.tile + p.pf * p.ngroups) * TILE_COLS, r0, pol_keep);
-                        if (p.hint) tma_load_2d_hint(xs_addr(s), &mapXp, full_bar(s), col0, r0, pol_keep);
-                        else tma_load_2d(xs_addr(s), &mapXp, full_bar(s), col0, r0);
+                            tma_prefetch_x_hint(&mapXp, (t.tile + p.pf * p.ngroups) * TILE_COLS, r0, p.xsh, pol_keep);
+                        if (p.hint) tma_load_x_hint(xs_addr(s), &mapXp, full_bar(s), col0, r0, p.xsh, pol_keep);
+                        else tma_load_x(xs_addr(s), &mapXp, full_bar(s), col0, r0, p.xsh);
                         tma_load_2d(bop(s), &mapW, full_bar(s), 0, r0);
                         tma_load_2d(bop(s) + R1 * 128, &mapW, full_bar(s), 32, r0);
                     } else {
@@ -345,10 +356,10 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
                         const int c0 = col0 + 32 * ch;
                         if (t.type == 1) {
                             const int r0 = row_slab + (it / F_BSEG) * 128;
-                            if (p.hint) tma_load_2d_hint(xs_addr(s), &mapXx, full_bar(s), c0, r0, pol_drop);
-                            else tma_load_2d(xs_addr(s), &mapXx, full_bar(s), c0, r0);
+                            if (p.hint) tma_load_x_hint(xs_addr(s), &mapXx, full_bar(s), c0, r0, p.xsh, pol_drop);
+                            else tma_load_x(xs_addr(s), &mapXx, full_bar(s), c0, r0, p.xsh);
                         } else {
-                            tma_load_2d(xs_addr(s), &mapHa, full_bar(s), c0, 0);
+                            tma_load_x(xs_addr(s), &mapHa, full_bar(s), c0, 0, kNoPanel);
                         }
                         tma_load_2d(bop(s), &mapHs, full_bar(s), 0, (c0 >> 5) * (2 * KP));
                     }
@@ -703,7 +714,7 @@ inline int fused_launch(FusedPlan& f, TcPlan& p, const DevState* st, const float
     fp.Cpart = f.Cpart; fp.tile_cnt = f.cnt; fp.tile_done = f.cnt + f.n_tiles;
     fp.ldh = p.ldh; fp.d = (int)p.d; fp.n_loc = (int)p.n_loc; fp.n_tiles = f.n_tiles;
     fp.nslab = f.nslab; fp.ngroups = f.ngroups; fp.depth = f.depth; fp.nslot = f.nslot; fp.hint = f.hint;
-    fp.pf = f.pf;
+    fp.pf = f.pf; fp.xsh = p.xsh;
     fp.wmean = p.center ? p.wmean : nullptr; fp.xsum = p.xsum;
     fp.fault = fault;
     fp.dbg = p.dbg;

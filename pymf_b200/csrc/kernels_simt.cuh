@@ -117,7 +117,7 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
                 const float* __restrict__ Hc, float* __restrict__ Hn, int64_t ldh,
                 int64_t d, int64_t n_loc, int kp, float lam, const float* __restrict__ Gneg,
                 int64_t rows_per_split, float* __restrict__ Cpart, unsigned* __restrict__ tickets,
-                float* __restrict__ zero_buf, int64_t zero_count) {
+                float* __restrict__ zero_buf, int64_t zero_count, int64_t xps, int xsh) {
     // Gneg != nullptr: Semi-NMF (pymf/snmf.py:72-90) - G is then G+ and Gneg is G-
     if (st->stop) return;
     if (zero_buf != nullptr) {   // clear the [X H^T | H H^T] partial buffer for the pass that follows (saves a k_zero launch)
@@ -142,7 +142,10 @@ k_h_update_simt(const DevState* __restrict__ st, const float* __restrict__ X, in
     const int nsplit = (int)gridDim.z;
     const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
     const int64_t r_end = nsplit > 1 ? min(d, r_begin + rows_per_split) : d;
-    tile_mac<KB>(c, W, kp, kb0, X, ldx, col0, n_loc, r_begin, r_end, Rs, Ls);       // W^T X (this CTA's rows)
+    {   // the 128-column tile lies inside one panel of X (common.cuh): panel-adjusted base, bound at the panel's end
+        const int64_t pend = ((col0 >> xsh) + 1) << xsh;
+        tile_mac<KB>(c, W, kp, kb0, X + xpanel_off(col0, xps, xsh), ldx, col0, min(n_loc, pend), r_begin, r_end, Rs, Ls);   // W^T X (this CTA's rows)
+    }
     if (nsplit > 1) {
         const int64_t tile_id = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
         float* part = Cpart + (tile_id * nsplit) * (KB * TILE_N);                  // [split][KB][TILE_N] of this tile
@@ -218,7 +221,8 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 k_ltr_partial_simt(const DevState* __restrict__ st, const float* __restrict__ L, int64_t ldl,
                    const float* __restrict__ R, int64_t ldr, int64_t r_ncols, int64_t rows,
                    int64_t rows_per_split, float* __restrict__ partial, int64_t out_ld,
-                   int64_t out_rows) {
+                   int64_t out_rows, int64_t rps = 0, int rsh = kNoPanelShift) {
+    // rps / rsh: panel layout of R when R is the data matrix X (common.cuh); row-major by default
     if (st->stop) return;
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
@@ -233,7 +237,8 @@ k_ltr_partial_simt(const DevState* __restrict__ st, const float* __restrict__ L,
     for (int i = 0; i < TK; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    tile_mac<KB>(acc, L, ldl, kb0, R, ldr, col0, r_ncols, r_begin, r_end, Rs, Ls);
+    tile_mac<KB>(acc, L, ldl, kb0, R + xpanel_off(col0, rps, rsh), ldr, col0, min(r_ncols, ((col0 >> rsh) + 1) << rsh),
+                 r_begin, r_end, Rs, Ls);
     float* out = partial + (int64_t)blockIdx.z * out_rows * out_ld;
     const int64_t col = col0 + tx * 4;
 #pragma unroll
@@ -267,7 +272,8 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t rows,
            const float* __restrict__ H, int64_t ldh, int64_t n_loc, int64_t cols_per_split,
            float* __restrict__ P, int64_t ldp, int nrb_x, int64_t rows_h, float* __restrict__ PB,
-           float* __restrict__ Ppart, int64_t part_stride, unsigned* __restrict__ tickets) {
+           float* __restrict__ Ppart, int64_t part_stride, unsigned* __restrict__ tickets,
+           int64_t xps = 0, int xsh = kNoPanelShift) {
     // Row blocks [0, nrb_x) of the grid compute X H^T; when PB != nullptr the remaining row blocks compute H H^T in
     // the same launch (the streamed operand is then H itself, rows_h rows, output PB) - one launch instead of two.
     // Column splits (gridDim.y) are combined DETERMINISTICALLY when Ppart != nullptr: every split parks its block in
@@ -276,7 +282,7 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
     // from run to run).  Ppart == nullptr: fp32 atomics into a cleared P.
     if (st->stop) return;
     const int64_t out_off = ((int)blockIdx.x >= nrb_x) ? (PB - P) : 0;
-    if ((int)blockIdx.x >= nrb_x) { X = H; ldx = ldh; rows = rows_h; P = PB; }
+    if ((int)blockIdx.x >= nrb_x) { X = H; ldx = ldh; rows = rows_h; P = PB; xps = 0; xsh = kNoPanelShift; }
     constexpr int TK = KB / 8;
     __shared__ float Xs[128][XHT_CK + 1];
     __shared__ __align__(16) float Hs[XHT_CK][KB];
@@ -302,7 +308,7 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
             int64_t r = row0 + row, c = c0 + c4 * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < rows && c < c_end) {
-                v = *reinterpret_cast<const float4*>(X + r * ldx + c);
+                v = *reinterpret_cast<const float4*>(X + xpanel_off(c0, xps, xsh) + r * ldx + c);   // 32-column chunk: one panel
                 if (c + 1 >= c_end) v.y = 0.f;
                 if (c + 2 >= c_end) v.z = 0.f;
                 if (c + 3 >= c_end) v.w = 0.f;
@@ -615,7 +621,7 @@ k_err(DevState* __restrict__ st, const float* __restrict__ W, const float* __res
 constexpr int XX_BLOCKS = 1184;   // 8 x 148
 __global__ void __launch_bounds__(256)
 k_xx(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t d, int64_t n_loc,
-     double* __restrict__ scratch /* XX_BLOCKS */) {
+     double* __restrict__ scratch /* XX_BLOCKS */, int64_t xps, int xsh) {
     __shared__ double s[256];
     __shared__ bool is_last;
     double acc = 0.0;
@@ -624,7 +630,7 @@ k_xx(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n4, c = (i % n4) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(X + r * ldx + c);
+        const float4 v = *reinterpret_cast<const float4*>(X + xpanel_off(c, xps, xsh) + r * ldx + c);
         float p = v.x * v.x;
         if (c + 1 < n_loc) p = fmaf(v.y, v.y, p);
         if (c + 2 < n_loc) p = fmaf(v.z, v.z, p);
@@ -675,7 +681,7 @@ template <int KB>
 __global__ void __launch_bounds__(SIMT_THREADS)
 k_resid_simt(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx,
              const float* __restrict__ Wt, int64_t ldwt, const float* __restrict__ H, int64_t ldh,
-             int64_t d, int64_t n_loc, int kp, double* __restrict__ partial) {
+             int64_t d, int64_t n_loc, int kp, double* __restrict__ partial, int64_t xps, int xsh) {
     if (st->stop) return;
     constexpr int TK = KB / 8;
     __shared__ __align__(16) float Rs[2][TILE_DK][TILE_N];
@@ -697,7 +703,7 @@ k_resid_simt(DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx
     for (int i = 0; i < TK; ++i) {
         const int64_t r = r0 + ty * TK + i;
         if (r < d && col < n_loc) {
-            const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + col);
+            const float4 x = *reinterpret_cast<const float4*>(X + xpanel_off(col0, xps, xsh) + r * ldx + col);
             float e = x.x - acc[i][0];
             s += (double)e * (double)e;
             if (col + 1 < n_loc) { e = x.y - acc[i][1]; s += (double)e * (double)e; }
@@ -743,12 +749,13 @@ __global__ void k_zero(const DevState* __restrict__ st, float* __restrict__ p, i
 // dst (rows x ldd, fp32) <- src (rows x cols, T contiguous with leading dimension lds)
 template <typename T>
 __global__ void k_cast_in(const T* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
-                          int64_t rows, int64_t cols) {
+                          int64_t rows, int64_t cols, int64_t dcol0 = 0, int64_t xps = 0, int xsh = kNoPanelShift) {
+    // dst element (r, dcol0 + c) of a matrix in the layout of common.cuh (row-major by default; dst = its base)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < rows * cols; i += stride) {
-        const int64_t r = i / cols, c = i % cols;
-        dst[r * ldd + c] = (float)src[r * lds + c];
+        const int64_t r = i / cols, c = dcol0 + i % cols;
+        dst[xpanel_off(c, xps, xsh) + r * ldd + c] = (float)src[r * lds + (c - dcol0)];
     }
 }
 template <typename T>
@@ -764,12 +771,12 @@ __global__ void k_cast_out(const float* __restrict__ src, int64_t lds, T* __rest
 
 // dst[r][c] = U[0,1) hash(seed, r * gen_ld + gen_col0 + c)  for r < rows, c < cols (pad stays 0)
 __global__ void k_gen_uniform(float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
-                              uint64_t seed, int64_t gen_ld, int64_t gen_col0) {
+                              uint64_t seed, int64_t gen_ld, int64_t gen_col0, int64_t xps = 0, int xsh = kNoPanelShift) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < rows * cols; i += stride) {
         const int64_t r = i / cols, c = i % cols;
-        dst[r * ldd + c] = hash_uniform(seed, (uint64_t)(r * gen_ld + gen_col0 + c));
+        dst[xpanel_off(c, xps, xsh) + r * ldd + c] = hash_uniform(seed, (uint64_t)(r * gen_ld + gen_col0 + c));
     }
 }
 

@@ -103,6 +103,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// Box of the data matrix X (or of H through a one-panel map): X maps are 3-D (column inside the panel, row, panel),
+// see "Layout of the data matrix" in common.cuh; xsh = log2(panel width), kNoPanel for a single panel.
+constexpr int kNoPanel = 31;
+__device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, int xsh) {
+    const int p = col >> xsh;
+    tma_load_3d(dst, map, bar, col - (p << xsh), row, p);
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -254,7 +266,8 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              int kh_rows, int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn) {
+              int kh_rows, int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn, int xsh) {
+    // xsh: log2 of the panel width of X (tma_load_x)
     // seg_c: stages per accumulation segment of the W^T X contraction (see "Segments" above)
     // kh_rows: rows of H contracted for G H (= the padded k of the whole problem).  For k <= 128 it equals KP;
     // for k > 128 the launch handles one 128-wide block of bases: mapH spans all kh_rows rows of H, mapG is the
@@ -309,7 +322,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         const CUtensorMap* ma = xphase ? &mapX : &mapH;
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_2d(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0);
+                        for (int c = 0; c < 4; ++c) tma_load_x(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0, xphase ? xsh : kNoPanel);
 #pragma unroll
                         for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
                     }
@@ -477,7 +490,7 @@ __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
          int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp,
-         float* __restrict__ Ppart, int64_t part_stride) {
+         float* __restrict__ Ppart, int64_t part_stride, int xsh) {
     // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
     // Ppart != nullptr: deterministic combine of the column splits - every task stores its sums in copy (task / num_rb)
     // of P's layout (part_stride floats apart) and k_sum_copies adds the copies in split order into P afterwards.
@@ -531,7 +544,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     mbar_wait(empty_bar(s), ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
-                        tma_load_2d(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0);
+                        tma_load_x(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0, xsh);
                         tma_load_2d(hch(s), &mapH, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));   // [H_hi ; H_lo] chunk
                     }
                     __syncwarp();
@@ -764,7 +777,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
               int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
-              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum) {
+              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum, int xsh) {
     // wmean != nullptr: the B operands are the CENTERED W / G (k_split_hilo_centered); the epilogue adds
     // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
@@ -824,7 +837,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #endif
                         const bool xphase = it < nd;
                         const int r0 = (xphase ? it : it - nd) * R1;
-                        tma_load_2d(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0);
+                        tma_load_x(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0, xphase ? xsh : kNoPanel);
 #if !defined(PYMFB_EXP_SKIP_WLOAD)
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
@@ -1048,7 +1061,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
          const __grid_constant__ CUtensorMap mapHA, const DevState* __restrict__ st,
          float* __restrict__ PA, float* __restrict__ PB, int d, int n_loc,
          int cols_per_task, int num_rb, int x_tasks, int hh_cols_per_task, int num_tasks,
-         float* __restrict__ dbg, float* __restrict__ PpartA, float* __restrict__ PpartB) {
+         float* __restrict__ dbg, float* __restrict__ PpartA, float* __restrict__ PpartB, int xsh) {
     // PpartA != nullptr: deterministic combine of the column splits (see k_xht_tc): copies of A are d * KP floats
     // apart, copies of B = H H^T (one per H H^T task) KP * KP floats; k_sum_copies then writes P.
     using Cfg = TsCfg<KP>;
@@ -1105,7 +1118,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     mbar_wait(empty_bar(s), ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
-                    tma_load_2d(xs_addr(s), ma, full_bar(s), c_begin + 32 * ch, row0);
+                    tma_load_x(xs_addr(s), ma, full_bar(s), c_begin + 32 * ch, row0, hh ? kNoPanel : xsh);
                     tma_load_2d(hch(s), &mapHs, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));
                 }
                 __syncwarp();
@@ -1359,9 +1372,10 @@ k_split_hilo_centered(const DevState* __restrict__ st, const float* __restrict__
 
 // xsum[c] = sum over the rows of X of column c (fp64 accumulation, stored fp32); once per data set
 __global__ void __launch_bounds__(256)
-k_colsum_x(const float* __restrict__ X, int64_t ldx, int64_t d, int64_t n_loc, float* __restrict__ xsum) {
+k_colsum_x(const float* __restrict__ X, int64_t ldx, int64_t d, int64_t n_loc, float* __restrict__ xsum, int64_t xps, int xsh) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_loc) return;
+    X += xpanel_off(c, xps, xsh);
     double a0 = 0.0, a1 = 0.0;
     int64_t r = 0;
     for (; r + 1 < d; r += 2) { a0 += (double)X[r * ldx + c]; a1 += (double)X[(r + 1) * ldx + c]; }
@@ -1378,6 +1392,9 @@ struct TcPlan {
     bool ready = false;
     int device = 0, sm_count = 148;
     int64_t d = 0, n_loc = 0, ldx = 0, ldh = 0;
+    int64_t xps = 0;           // layout of X (common.cuh): floats between panels, 0 = row-major
+    int xsh64 = kNoPanelShift; // log2(panel width) for 64-bit column arithmetic (SIMT helpers)
+    int xsh = tc::kNoPanel;    // the same for the TMA coordinates of the tensor-core kernels
     int k = 0, kp = 0;
     const float* X = nullptr;
     const float* Hbuf[2] = {nullptr, nullptr};
@@ -1442,6 +1459,26 @@ inline bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return false; }
+    return true;
+}
+
+// 3-D map of a matrix in the layout of common.cuh: dims (columns inside a panel, rows, panels).  swz: 0 = none (plain
+// box), 1 = SWIZZLE_128B (K-major operand), 2 = SWIZZLE_128B_ATOM_32B (MN-major operand).  Row-major = one panel.
+inline bool make_map3(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int64_t xps, int xsh,
+                      int box_cols, int box_rows, int swz, std::string* err) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+    const bool paneled = xps != 0;
+    const int64_t pw = paneled ? ((int64_t)1 << xsh) : cols;
+    const int64_t npan = paneled ? (cols + pw - 1) / pw : 1;
+    cuuint64_t dims[3] = {(cuuint64_t)pw, (cuuint64_t)rows, (cuuint64_t)npan};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)(paneled ? xps : ld * rows) * sizeof(float)};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUtensorMapSwizzle sw = swz == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swz == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled(3-D) failed with code " + std::to_string((int)r); return false; }
     return true;
 }
 
@@ -1525,9 +1562,10 @@ inline void tc_release(TcPlan& p) {
 }
 
 inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc, int k, int kp, const float* X,
-                   int64_t ldx, int64_t ldh, const float* H0, const float* H1) {
+                   int64_t ldx, int64_t ldh, const float* H0, const float* H1, int64_t xps, int xsh64) {
     tc_release(p);
     p.device = device; p.sm_count = sm_count; p.d = d; p.n_loc = n_loc; p.k = k; p.kp = kp; p.X = X; p.ldx = ldx; p.ldh = ldh;
+    p.xps = xps; p.xsh64 = xsh64; p.xsh = xps != 0 ? xsh64 : tc::kNoPanel;
     p.Hbuf[0] = H0; p.Hbuf[1] = H1;
     p.nblk = kp > 128 ? kp / 128 : 1;
     p.kpb = kp > 128 ? 128 : kp;
@@ -1539,8 +1577,8 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         p.hs_valid[i] = false;
     }
     bool ok = true;
-    ok = ok && make_map(&p.mapX_h, X, d, n_loc, ldx, tc::R1, true, &p.err);
-    ok = ok && make_map(&p.mapX_x, X, d, n_loc, ldx, 128, false, &p.err);
+    ok = ok && make_map3(&p.mapX_h, X, d, n_loc, ldx, xps, xsh64, 32, tc::R1, 2, &p.err);
+    ok = ok && make_map3(&p.mapX_x, X, d, n_loc, ldx, xps, xsh64, 32, 128, 1, &p.err);
     ok = ok && make_map(&p.mapW, p.Wsplit, d, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
     ok = ok && make_map(&p.mapG, p.Gsplit, kp, 2 * p.kpb, 2 * p.kpb, tc::R1, true, &p.err);
     for (int b = 0; b < p.nblk; ++b) {
@@ -1550,12 +1588,12 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
             ok = ok && make_map(&p.mapH_xb[i][b], p.Hs[i] + (size_t)b * 2 * p.kpb * ldh, (ldh / 32) * 2 * p.kpb, 32, 32, 2 * p.kpb, false, &p.err);
     }
     for (int i = 0; i < 2; ++i) {
-        ok = ok && make_map(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, tc::R1, true, &p.err);
+        ok = ok && make_map3(&p.mapH_h[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, 32, tc::R1, 2, &p.err);
         ok = ok && make_map(&p.mapH_x[i], p.Hs[i], (ldh / 32) * 2 * p.kpb, 32, 32, 2 * p.kpb, false, &p.err);   // [H_hi ; H_lo] chunks as B (block 0)
-        ok = ok && make_map(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 128, false, &p.err);        // H as A
+        ok = ok && make_map3(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, 32, 128, 1, &p.err);        // H as A
     }
-    ok = ok && make_map_plain(&p.mapX_p, X, d, n_loc, ldx, tc::TILE_COLS, tc::R1, &p.err);
-    for (int i = 0; i < 2; ++i) ok = ok && make_map_plain(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, tc::TILE_COLS, tc::R1, &p.err);
+    ok = ok && make_map3(&p.mapX_p, X, d, n_loc, ldx, xps, xsh64, tc::TILE_COLS, tc::R1, 0, &p.err);
+    for (int i = 0; i < 2; ++i) ok = ok && make_map3(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, tc::TILE_COLS, tc::R1, 0, &p.err);
     if (!ok) return 1;
     {
         const char* force_ss = getenv("PYMFB_TC_FORCE_SS");
@@ -1641,7 +1679,7 @@ inline int tc_after_gram(TcPlan& p, const DevState* st, const float* W, const fl
     const int64_t nw = p.d * p.kpb, ng = (int64_t)p.kp * p.kpb;
     if (p.center) {        // nblk == 1, kpb == kp
         if (!p.xsum_valid) {
-            tc::k_colsum_x<<<(unsigned)((p.n_loc + 255) / 256), 256, 0, stream>>>(p.X, p.ldx, p.d, p.n_loc, p.xsum);
+            tc::k_colsum_x<<<(unsigned)((p.n_loc + 255) / 256), 256, 0, stream>>>(p.X, p.ldx, p.d, p.n_loc, p.xsum, p.xps, p.xsh64);
             p.xsum_valid = true;
             *launches += 1;
         }
@@ -1670,7 +1708,7 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
         tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_h, p.mapW_b[b], p.mapH_h[hsrc], p.mapG_b[b], st, p.Hbuf[hsrc] + hoff, Hn + hoff, p.Hs[hsrc ^ 1] + 2 * hoff,
             p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.seg_c, p.lam_h,
-            p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr);
+            p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr, p.xsh);
     }
 }
 // experiment knob: PYMFB_GRID caps the CTA count of the H-update kernels (per-SM pipeline capacity measurements)
@@ -1683,7 +1721,7 @@ inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
     const int grid = grid_cap(std::min(p.h_tiles, p.sm_count));
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.seg_c, p.lam_h, p.Dp, p.Dn,
-        p.center ? p.wmean : nullptr, p.gmean, p.xsum);
+        p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
 }
 template <int KP>
 inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaStream_t stream) {
@@ -1691,7 +1729,7 @@ inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     const int grid = std::min(ntasks, p.sm_count);
     tc::k_xht_ts<KP><<<grid, tc::X_THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_x, p.mapH_x[hsrc], p.mapH_a[hsrc], st, P, P + p.d * p.kp, (int)p.d, (int)p.n_loc, p.x_cols_per_task,
-        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg, p.xpart, p.xpartB);
+        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg, p.xpart, p.xpartB, p.xsh);
 }
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
@@ -1717,7 +1755,7 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
-            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp);
+            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh);
 }
 // true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
 // extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
@@ -1731,7 +1769,7 @@ inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cu
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
-            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp);
+            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;

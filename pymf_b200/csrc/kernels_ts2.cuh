@@ -91,7 +91,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
               int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
-              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum) {
+              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum, int xsh) {
     // wmean != nullptr: the B operands are the CENTERED W / G (k_split_hilo_centered); the epilogue adds
     // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
@@ -157,7 +157,7 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::BSTAGE_BYTES);
                         const bool xphase = it < nd;
                         const int r0 = (xphase ? it : it - nd) * R1;
-                        tma_load_2d(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0);
+                        tma_load_x(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0, xphase ? xsh : kNoPanel);
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
                         // region B (operand of a_hi x [b_hi|b_lo], N = 2KP over the pair): this CTA's KP columns = b_hi
                         // for rank 0, b_lo for rank 1; region A (operand of a_lo x b_hi, N = KP): this CTA's half of b_hi
@@ -387,11 +387,11 @@ inline int ts2_h_update(TcPlan& p, const DevState* st, const float* Hc, float* H
     if (p.kp == 64)
         tc::k_h_update_ts2<64><<<grid, tc::Ts2Cfg<64>::THREADS, tc::Ts2Cfg<64>::SMEM_BYTES, stream>>>(
             p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
-            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum);
+            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
     else
         tc::k_h_update_ts2<32><<<grid, tc::Ts2Cfg<32>::THREADS, tc::Ts2Cfg<32>::SMEM_BYTES, stream>>>(
             p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
-            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum);
+            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

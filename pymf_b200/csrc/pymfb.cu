@@ -158,6 +158,11 @@ struct pymfb_ctx {
 
     const float* X = nullptr;      // d x ldx
     float* X_own = nullptr;
+    int64_t own_ldx = 0, own_xps = 0;    // layout of X_own (ensure_own_x)
+    int own_xsh = kNoPanelShift;
+    size_t own_bytes = 0;
+    int64_t xps = 0;               // layout of X (common.cuh): floats between column panels, 0 = row-major
+    int xsh = kNoPanelShift;       // log2(panel width)
     int64_t ldx = 0;
 
     float* W[2] = {nullptr, nullptr};   // d x kp
@@ -265,7 +270,7 @@ static inline int grid_for(int64_t count, int block, int cap) {
 }
 
 static int plan_tc(pymfb_ctx* c) {
-    if (tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1]))
+    if (tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1], c->xps, c->xsh))
         return fail("tcgen05 plan failed: %s", c->tc.err.c_str());
     if (ts2_prepare(c->tc)) return fail("CTA-pair kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     fused_release(c->fused);
@@ -380,12 +385,12 @@ static int launch_h_update(pymfb_ctx* c) {
             k_h_update_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
                                                                       c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
-                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count);
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count, c->xps, c->xsh);
         else
             k_h_update_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->W[c->wcur], snmf ? c->Gpos : c->G,
                                                                       c->H[c->hcur], c->H[c->hcur ^ 1], c->ldh,
                                                                       c->d, c->n_loc, c->kp, (float)c->lam_h, snmf ? c->Gneg : nullptr,
-                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count);
+                                                                      c->h_rows_per_split, c->h_cpart, c->h_tickets, c->P, c->ab_count, c->xps, c->xsh);
         c->launches += 1;
         CU(cudaGetLastError());
         c->p_zeroed = true;            // the SIMT kernel cleared P (nothing reads [A | B] between here and the next X H^T pass)
@@ -453,10 +458,10 @@ static int launch_xht(pymfb_ctx* c) {
         float* PB = c->P + c->d * c->kp;
         if (c->kb == 16)
             k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
-                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt);
+                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt, c->xps, c->xsh);
         else
             k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
-                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt);
+                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt, c->xps, c->xsh);
         c->launches += 1;
         CU(cudaGetLastError());
     }
@@ -468,7 +473,7 @@ static int launch_xht(pymfb_ctx* c) {
 }
 
 static int launch_xx(pymfb_ctx* c) {
-    k_xx<<<XX_BLOCKS, 256, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, c->n_loc, c->red_scratch);
+    k_xx<<<XX_BLOCKS, 256, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, c->n_loc, c->red_scratch, c->xps, c->xsh);
     c->launches += 1;
     CU(cudaGetLastError());
     if (c->world > 1)
@@ -485,9 +490,9 @@ static int launch_err(pymfb_ctx* c, bool store, bool early_stop) {
         k_transpose_w<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->st, c->W[c->wcur], c->d, c->kp, c->Wt, c->ldwt);
         dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)((c->d + c->kb - 1) / c->kb));
         if (c->kb == 16)
-            k_resid_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part);
+            k_resid_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part, c->xps, c->xsh);
         else
-            k_resid_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part);
+            k_resid_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->Wt, c->ldwt, c->H[c->hcur], c->ldh, c->d, c->n_loc, c->kp, c->resid_part, c->xps, c->xsh);
         c->launches += 2;
         CU(cudaGetLastError());
         if (c->world > 1)
@@ -910,13 +915,30 @@ static int data_changed(pymfb_ctx* c) {
     return 0;
 }
 
+// Context-owned copy of X.  Wide matrices (row stride of the row-major layout above 256 KB) on tensor-path shapes are
+// stored panel-major (common.cuh): column panels of 4096 columns, each a dense d x 4096 block, so that the 128 rows
+// of a TMA box share one 2 MB page.  PYMFB_XPANEL=0 keeps everything row-major, =<log2 width> picks another width.
 static int ensure_own_x(pymfb_ctx* c) {
     if (!c->X_own) {
-        c->ldx = padded_ld(c->n_loc);
-        CU(cudaMalloc(&c->X_own, (size_t)c->d * c->ldx * sizeof(float)));
-        CU(cudaMemsetAsync(c->X_own, 0, (size_t)c->d * c->ldx * sizeof(float), c->stream));
+        int sh = 12;
+        bool want = c->n_loc > 65536 && c->d >= 64 && c->kp % 32 == 0 && c->kp <= 512;
+        if (const char* e = getenv("PYMFB_XPANEL")) {     // 0: never; 7..20: panels of 2^v columns whatever n is (tests)
+            const int v = atoi(e);
+            if (v <= 0) want = false;
+            else if (v >= 7 && v <= 20) { sh = v; want = c->d >= 64 && c->n_loc >= 128 && c->kp % 32 == 0 && c->kp <= 512; }
+        }
+        if (want) {
+            const int64_t pw = (int64_t)1 << sh, npan = (c->n_loc + pw - 1) / pw;
+            c->own_ldx = pw; c->own_xps = c->d * pw; c->own_xsh = sh;
+            c->own_bytes = (size_t)npan * c->d * pw * sizeof(float);
+        } else {
+            c->own_ldx = padded_ld(c->n_loc); c->own_xps = 0; c->own_xsh = kNoPanelShift;
+            c->own_bytes = (size_t)c->d * c->own_ldx * sizeof(float);
+        }
+        CU(cudaMalloc(&c->X_own, c->own_bytes));
+        CU(cudaMemsetAsync(c->X_own, 0, c->own_bytes, c->stream));
     }
-    c->ldx = padded_ld(c->n_loc);
+    c->ldx = c->own_ldx; c->xps = c->own_xps; c->xsh = c->own_xsh;
     c->X = c->X_own;
     return 0;
 }
@@ -927,7 +949,7 @@ int pymfb_bind_x(pymfb_ctx* c, const float* x_dev, int64_t ld) {
     if (ld < c->n_loc || (ld % 4) != 0) return fail("leading dimension %lld must be >= n_local and a multiple of 4", (long long)ld);
     if (((uintptr_t)x_dev & 15) != 0) return fail("x_dev must be 16-byte aligned");
     CU(cudaSetDevice(c->device));
-    c->X = x_dev; c->ldx = ld;
+    c->X = x_dev; c->ldx = ld; c->xps = 0; c->xsh = kNoPanelShift;
     return data_changed(c);
 }
 
@@ -962,6 +984,14 @@ static void stream_copy(void* dst, const void* src, size_t n) {
 // Host -> device ingest of X: a ring of pinned staging buffers is filled by a
 // few host threads (pageable user memory -> pinned) while the previous chunk's H2D copy (and the
 // fp64 -> fp32 cast kernel) run on the context's stream.
+// The pinned staging ring is kept by the PROCESS between uploads (3 x 64 MiB): allocating and page-locking it costs
+// ~50 ms, which on a 4 GiB upload was a fifth of the whole ingest.  One upload at a time uses it; a concurrent
+// second upload (another context on another thread) allocates its own.
+static std::mutex g_ring_mu;
+static void* g_ring[3] = {nullptr, nullptr, nullptr};
+static size_t g_ring_bytes = 0;
+static bool g_ring_busy = false;
+
 static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
     const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
     const int64_t row_bytes = c->n_loc * (int64_t)esz;
@@ -973,13 +1003,15 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
     void* dstage[NB] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
     int rc = 0;
+    bool own_ring = false;                      // this call took the process ring (give it back, do not free it)
     auto cleanup = [&]() {
         cudaStreamSynchronize(c->stream);
         for (int b = 0; b < NB; ++b) {
-            if (pinned[b]) pymfb_host_free(pinned[b]);
+            if (pinned[b] && !own_ring) pymfb_host_free(pinned[b]);
             if (dstage[b]) cudaFree(dstage[b]);
             if (ev[b]) cudaEventDestroy(ev[b]);
         }
+        if (own_ring) { std::lock_guard<std::mutex> lk(g_ring_mu); g_ring_busy = false; }
     };
 #define UP(call)                                                                                   \
     do {                                                                                           \
@@ -990,9 +1022,27 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
             return rc;                                                                             \
         }                                                                                          \
     } while (0)
+    {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        if (!g_ring_busy) {
+            if (g_ring_bytes < buf_bytes) {
+                for (int b = 0; b < NB; ++b) { if (g_ring[b]) pymfb_host_free(g_ring[b]); g_ring[b] = nullptr; }
+                g_ring_bytes = 0;
+                bool ok = true;
+                for (int b = 0; b < NB && ok; ++b) ok = pymfb_host_alloc(&g_ring[b], buf_bytes) == 0;
+                if (ok) g_ring_bytes = buf_bytes;
+                else for (int b = 0; b < NB; ++b) { if (g_ring[b]) pymfb_host_free(g_ring[b]); g_ring[b] = nullptr; }
+            }
+            if (g_ring_bytes >= buf_bytes) {
+                for (int b = 0; b < NB; ++b) pinned[b] = g_ring[b];
+                g_ring_busy = true;
+                own_ring = true;
+            }
+        }
+    }
     for (int b = 0; b < NB; ++b) {
-        if (pymfb_host_alloc(&pinned[b], buf_bytes)) { cleanup(); return 1; }
-        if (dtype == PYMFB_F64) UP(cudaMalloc(&dstage[b], buf_bytes));
+        if (!own_ring && pymfb_host_alloc(&pinned[b], buf_bytes)) { cleanup(); return 1; }
+        if (dtype == PYMFB_F64 || c->xps != 0) UP(cudaMalloc(&dstage[b], buf_bytes));   // cast and / or panel scatter on the device
         UP(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
     }
     unsigned hw = std::thread::hardware_concurrency();
@@ -1017,13 +1067,16 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
             }
             for (auto& t : th) t.join();
         }
-        if (dtype == PYMFB_F32) {
+        if (dtype == PYMFB_F32 && c->xps == 0) {
             UP(cudaMemcpy2DAsync(c->X_own + r0 * c->ldx, c->ldx * sizeof(float), pinned[b], row_bytes, row_bytes, nr,
                                  cudaMemcpyHostToDevice, c->stream));
         } else {
             UP(cudaMemcpyAsync(dstage[b], pinned[b], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, c->stream));
-            k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-                (const double*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
+            const int g = grid_for(nr * c->n_loc, 256, 16 * c->sm_count);
+            if (dtype == PYMFB_F32)
+                k_cast_in<float><<<g, 256, 0, c->stream>>>((const float*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
+            else
+                k_cast_in<double><<<g, 256, 0, c->stream>>>((const double*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
             c->launches += 1;
             UP(cudaGetLastError());
         }
@@ -1047,7 +1100,14 @@ static bool host_is_pinned(const void* p) {
 // the next chunk is in flight.
 static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
     if (dtype == PYMFB_F32) {
-        if (ld == c->n_loc && c->ldx == c->n_loc)
+        if (c->xps != 0) {             // panel-major X: one strided DMA per column panel
+            const int64_t pw = (int64_t)1 << c->xsh;
+            for (int64_t c0 = 0; c0 < c->n_loc; c0 += pw) {
+                const int64_t w = std::min(pw, c->n_loc - c0);
+                CU(cudaMemcpy2DAsync(c->X_own + (c0 >> c->xsh) * c->xps, c->ldx * sizeof(float), (const float*)host + c0, (size_t)ld * sizeof(float),
+                                     (size_t)w * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+            }
+        } else if (ld == c->n_loc && c->ldx == c->n_loc)
             CU(cudaMemcpyAsync(c->X_own, host, (size_t)c->d * c->n_loc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         else
             CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float),
@@ -1094,7 +1154,7 @@ static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
         UP(cudaEventRecord(copied, copy_stream));
         UP(cudaStreamWaitEvent(c->stream, copied, 0));
         k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-            dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc);
+            dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
         c->launches += 1;
         UP(cudaGetLastError());
         UP(cudaEventRecord(cast_done[b], c->stream));
@@ -1141,8 +1201,14 @@ int pymfb_upload_x_panel(pymfb_ctx* c, const void* host, int dtype, int64_t ld, 
     CU(cudaSetDevice(c->device));
     if (!host_is_pinned(host)) c->last_upload_pinned = false;      // the runtime stages pageable panels itself (synchronous)
     if (dtype == PYMFB_F32) {
-        CU(cudaMemcpy2DAsync(c->X_own + col0, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float), (size_t)ncols * sizeof(float),
-                             (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+        // split at the panel boundaries of the device layout (one piece when X is row-major)
+        for (int64_t a = col0; a < col0 + ncols;) {
+            const int64_t pend = ((a >> c->xsh) + 1) << c->xsh;
+            const int64_t w = std::min(col0 + ncols, pend) - a;
+            CU(cudaMemcpy2DAsync(c->X_own + xpanel_off(a, c->xps, c->xsh) + a, c->ldx * sizeof(float), (const float*)host + (a - col0),
+                                 (size_t)ld * sizeof(float), (size_t)w * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+            a += w;
+        }
     } else {
         const size_t need = (size_t)c->d * ncols * sizeof(double);
         if (need > c->panel_stage_bytes[slot]) {
@@ -1155,7 +1221,7 @@ int pymfb_upload_x_panel(pymfb_ctx* c, const void* host, int dtype, int64_t ld, 
         CU(cudaMemcpy2DAsync(c->panel_stage[slot], (size_t)ncols * sizeof(double), host, (size_t)ld * sizeof(double),
                              (size_t)ncols * sizeof(double), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
         k_cast_in<double><<<grid_for(c->d * ncols, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-            (const double*)c->panel_stage[slot], ncols, c->X_own + col0, c->ldx, c->d, ncols);
+            (const double*)c->panel_stage[slot], ncols, c->X_own, c->ldx, c->d, ncols, col0, c->xps, c->xsh);
         c->launches += 1;
         CU(cudaGetLastError());
     }
@@ -1261,7 +1327,7 @@ int pymfb_gen_x(pymfb_ctx* c, uint64_t seed) {
     CU(cudaSetDevice(c->device));
     CK(ensure_own_x(c));
     k_gen_uniform<<<grid_for(c->d * c->n_loc, 256, 32 * c->sm_count), 256, 0, c->stream>>>(
-        c->X_own, c->ldx, c->d, c->n_loc, seed, c->n_glob, c->col0);
+        c->X_own, c->ldx, c->d, c->n_loc, seed, c->n_glob, c->col0, c->xps, c->xsh);
     c->launches += 1;
     CU(cudaGetLastError());
     return data_changed(c);
@@ -1427,8 +1493,9 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
     };
     // Out (b x n) = L^T In with L b x b row-major (L[j][i]):  Out[i][col] = sum_j L[j][i] In[j][col]
     auto left_mul_t = [&](const float* L, int64_t ldl, int64_t rows, const float* In, int64_t ldin, float* Out) {
+        const bool is_x = In == c->X;                             // the data matrix may be panel-major
         k_ltr_partial_simt<32><<<dim3((unsigned)((n + TILE_N - 1) / TILE_N), (unsigned)kblocks, 1), SIMT_THREADS, 0, s>>>(
-            c->st, L, ldl, In, ldin, n, rows, rows, Out, ldz, b);
+            c->st, L, ldl, In, ldin, n, rows, rows, Out, ldz, b, is_x ? c->xps : 0, is_x ? c->xsh : kNoPanelShift);
         c->launches += 1;
     };
     auto orthonormalise = [&](const float* A, float* Out) {      // Out = A L^-T with L L^T = A^T A
@@ -1452,7 +1519,7 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
         rayleigh_ritz();
         left_mul_t(Rm, b, b, Zt, ldz, Zt2);                      // rows of Zt2: (Ritz vector)^T X
         k_xht_simt<32><<<dim3((unsigned)rowblocks, ns, (unsigned)kblocks), SIMT_THREADS, 0, s>>>(
-            c->st, c->X, c->ldx, d, Zt2, ldz, n, cps, Y, b, (int)rowblocks, 0, nullptr, Ppart, d * b, tickets);
+            c->st, c->X, c->ldx, d, Zt2, ldz, n, cps, Y, b, (int)rowblocks, 0, nullptr, Ppart, d * b, tickets, c->xps, c->xsh);
         c->launches += 1;
         orthonormalise(Y, Q);                                    // Y = X X^T (Ritz vectors) -> next Q
         SV(cudaGetLastError());

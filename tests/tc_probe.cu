@@ -111,7 +111,7 @@ static int timing_mode(int64_t d, int64_t n, int KPv, int reps, int64_t pad) {
     CHECK(cudaMalloc(&dH1, KPv * ldh * 4)); CHECK(cudaMemset(dH1, 0, KPv * ldh * 4));
     CHECK(cudaMalloc(&dP, (d * KPv + KPv * KPv) * 4)); CHECK(cudaMemset(dP, 0, (d * KPv + KPv * KPv) * 4));
     TcPlan p;
-    if (tc_plan(p, 0, 148, d, n, KPv, KPv, dX, ldx, ldh, dH0, dH1)) { printf("plan failed: %s\n", p.err.c_str()); return 1; }
+    if (tc_plan(p, 0, 148, d, n, KPv, KPv, dX, ldx, ldh, dH0, dH1, 0, pymfb::kNoPanelShift)) { printf("plan failed: %s\n", p.err.c_str()); return 1; }
     int64_t launches = 0;
     tc_after_gram(p, st, dW, dG, 0, &launches);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -154,7 +154,7 @@ int main(int argc, char** argv) {
         auto G = fill(KP, KP, KP, cs.g);
         float *dX = up(X), *dW = up(W), *dH0 = up(H), *dH1 = up(H), *dG = up(G);
         TcPlan p;
-        if (tc_plan(p, 0, 148, d, n, KP, KP, dX, ldx, ldh, dH0, dH1)) { printf("plan failed: %s\n", p.err.c_str()); return 1; }
+        if (tc_plan(p, 0, 148, d, n, KP, KP, dX, ldx, ldh, dH0, dH1, 0, pymfb::kNoPanelShift)) { printf("plan failed: %s\n", p.err.c_str()); return 1; }
         p.dbg = dbg;
         int64_t launches = 0;
         tc_after_gram(p, st, dW, dG, 0, &launches);

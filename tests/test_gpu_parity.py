@@ -598,3 +598,52 @@ def test_trace_identity_hands_over_to_the_direct_residual_when_it_cancels():
     Wr, Hr = W.copy(), H.copy()
     fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=3)
     assert np.max(np.abs(m.ferr - fr) / fr) < TOL_FERR
+
+
+@pytest.mark.parametrize("shape", [(300, 1000, 20), (512, 4100, 32), (1024, 2500, 128), (256, 3000, 64)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_panel_major_x_equals_row_major_x(shape, dtype, monkeypatch):
+    """Wide context-owned matrices are stored panel-major (column panels of 4096 columns, common.cuh) so that a TMA
+    box stays inside one page; PYMFB_XPANEL=7 forces 128-column panels on a small matrix.  Every reader of X (both
+    kernel families, ||X||^2, the direct residual, the column sums, NNDSVD) and every ingest path (pinned, pageable,
+    h5py-like panels) must see the same matrix: one H update is bit-identical, trajectories match the oracle."""
+    from tests.test_host_logic import RecordingSource
+    d, n, k = shape
+    rng = np.random.RandomState(n)
+    X = rng.random_sample((d, n)).astype(dtype)
+    W0 = rng.random_sample((d, k)); H0 = rng.random_sample((k, n))
+    Xp = pymf_b200.pinned_empty((d, n), dtype); Xp[...] = X
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=3, early_stop=False)
+    res = {}
+    for layout in ("0", "7"):
+        monkeypatch.setenv("PYMFB_XPANEL", layout)
+        for path in ("simt", "tc"):
+            for src_name, data in (("pageable", X), ("pinned", Xp), ("panels", RecordingSource(X))):
+                m = pymf_b200.NMF(data, num_bases=k, path=path)
+                m.W, m.H = W0.copy(), H0.copy()
+                m.factorize(niter=1, compute_w=False, compute_err=False)
+                h1 = m.H.copy()
+                m.W, m.H = W0.copy(), H0.copy()
+                m._engine.set_err_mode("trace")
+                m.factorize(niter=3)
+                f_trace = m.ferr.copy()
+                m._engine.set_err_mode("direct")
+                f_direct = m.frobenius_norm()
+                res[(layout, path, src_name)] = (h1, m.W.copy(), m.H.copy(), f_trace, f_direct)
+                assert rel(m.W, Wr) < TOL_WH and rel(m.H, Hr) < TOL_WH, (layout, path, src_name)
+                assert np.max(np.abs(f_trace - fr) / fr) < TOL_FERR and abs(f_direct - fr[-1]) / fr[-1] < TOL_FERR
+    for path in ("simt", "tc"):
+        ref = res[("0", path, "pageable")]
+        for key, val in res.items():
+            if key[1] == path:
+                np.testing.assert_array_equal(val[0], ref[0], err_msg=str(key))     # one H update: bit-identical
+                np.testing.assert_array_equal(val[1], ref[1], err_msg=str(key))     # deterministic combine: W too
+                np.testing.assert_array_equal(val[3], ref[3], err_msg=str(key))
+    # NNDSVD reads X through the same layout
+    monkeypatch.setenv("PYMFB_XPANEL", "0")
+    a = pymf_b200.NNDSVD(X, num_bases=min(k, 8)); a.factorize()
+    monkeypatch.setenv("PYMFB_XPANEL", "7")
+    b = pymf_b200.NNDSVD(X, num_bases=min(k, 8)); b.factorize()
+    np.testing.assert_array_equal(a.W, b.W)
+    np.testing.assert_array_equal(a.H, b.H)
