@@ -758,6 +758,31 @@ __global__ void k_cast_in(const T* __restrict__ src, int64_t lds, float* __restr
         dst[xpanel_off(c, xps, xsh) + r * ldd + c] = (float)src[r * lds + (c - dcol0)];
     }
 }
+// Ingest: rows x cols block of a host-layout staging buffer (element type T, leading dimension lds) -> X in the
+// layout of common.cuh at (row, dcol0 + col); dst is X's base advanced by (first row) * ldd.  One thread moves four
+// consecutive columns (cols and dcol0 are multiples of 4 except for the ragged tail), blockIdx.y strides the rows:
+// no integer division per element (k_cast_in's i / cols made the scatter of a 64 MiB chunk cost as much as its DMA).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_place_x(const T* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols,
+          int64_t dcol0, int64_t xps, int xsh) {
+    const int64_t c4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c4 >= cols) return;
+    const int64_t c = dcol0 + c4;
+    float* out = dst + xpanel_off(c, xps, xsh) + c;
+    const bool vec = c4 + 3 < cols && ((c & 3) == 0) && ((ldd & 3) == 0) && ((xps & 3) == 0);
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const T* in = src + r * lds + c4;
+        if (vec) {
+            *reinterpret_cast<float4*>(out + r * ldd) = make_float4((float)in[0], (float)in[1], (float)in[2], (float)in[3]);
+        } else {
+            for (int j = 0; j < 4 && c4 + j < cols; ++j) {
+                const int64_t cj = c + j;
+                dst[xpanel_off(cj, xps, xsh) + r * ldd + cj] = (float)in[j];
+            }
+        }
+    }
+}
 template <typename T>
 __global__ void k_cast_out(const float* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd,
                            int64_t rows, int64_t cols) {

@@ -646,6 +646,14 @@ static int enqueue_iterations(pymfb_ctx* c, int niter, unsigned flags) {
     return 0;
 }
 
+// stage (rows x cols of T, leading dimension lds) -> X_own rows [r0, r0 + rows), columns [dcol0, dcol0 + cols)
+template <typename T>
+static void launch_place_x(pymfb_ctx* c, const T* stage, int64_t lds, int64_t r0, int64_t rows, int64_t cols, int64_t dcol0) {
+    dim3 grid((unsigned)((cols + 1023) / 1024), (unsigned)std::min<int64_t>(rows, 4096));
+    k_place_x<T><<<grid, 256, 0, c->stream>>>(stage, lds, c->X_own + r0 * c->ldx, c->ldx, rows, cols, dcol0, c->xps, c->xsh);
+    c->launches += 1;
+}
+
 static int p_unregister(pymfb_ctx* c) {
     if (c->p_reg && c->comm && g_nccl.CommDeregister) g_nccl.CommDeregister(c->comm, c->p_reg);
     c->p_reg = nullptr;
@@ -915,13 +923,16 @@ static int data_changed(pymfb_ctx* c) {
     return 0;
 }
 
-// Context-owned copy of X.  Wide matrices (row stride of the row-major layout above 256 KB) on tensor-path shapes are
-// stored panel-major (common.cuh): column panels of 4096 columns, each a dense d x 4096 block, so that the 128 rows
-// of a TMA box share one 2 MB page.  PYMFB_XPANEL=0 keeps everything row-major, =<log2 width> picks another width.
+// Context-owned copy of X.  Streaming-sized matrices on tensor-path shapes are stored panel-major (common.cuh): column
+// panels of 128 columns, each a dense d x 128 block.  A column tile of the H-update pass is then ONE contiguous
+// d x 512 B region, and the 128-row boxes of the X H^T pass sit 512 B apart instead of a whole row (4 MB at
+// n = 2^20: 128 pages of 2 MB per box).  Same-box A/B against row-major (ms per iteration): cfg3 53.5 -> 50.4,
+// cfg4 k=64 8.44 -> 7.83, cfg5 33.7 -> 31.4, cfg2 1.443 -> 1.405; wider panels (512 .. 16384 columns) gave less.
+// PYMFB_XPANEL=0 keeps everything row-major, =<log2 width> picks another width.
 static int ensure_own_x(pymfb_ctx* c) {
     if (!c->X_own) {
-        int sh = 12;
-        bool want = c->n_loc > 65536 && c->d >= 64 && c->kp % 32 == 0 && c->kp <= 512;
+        int sh = 7;
+        bool want = (double)c->d * (double)c->n_loc >= 16777216.0 && c->d >= 64 && c->n_loc >= 128 && c->kp % 32 == 0 && c->kp <= 512;
         if (const char* e = getenv("PYMFB_XPANEL")) {     // 0: never; 7..20: panels of 2^v columns whatever n is (tests)
             const int v = atoi(e);
             if (v <= 0) want = false;
@@ -1072,12 +1083,8 @@ static int staged_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
                                  cudaMemcpyHostToDevice, c->stream));
         } else {
             UP(cudaMemcpyAsync(dstage[b], pinned[b], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, c->stream));
-            const int g = grid_for(nr * c->n_loc, 256, 16 * c->sm_count);
-            if (dtype == PYMFB_F32)
-                k_cast_in<float><<<g, 256, 0, c->stream>>>((const float*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
-            else
-                k_cast_in<double><<<g, 256, 0, c->stream>>>((const double*)dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
-            c->launches += 1;
+            if (dtype == PYMFB_F32) launch_place_x<float>(c, (const float*)dstage[b], c->n_loc, r0, nr, c->n_loc, 0);
+            else launch_place_x<double>(c, (const double*)dstage[b], c->n_loc, r0, nr, c->n_loc, 0);
             UP(cudaGetLastError());
         }
         UP(cudaEventRecord(ev[b], c->stream));
@@ -1099,25 +1106,21 @@ static bool host_is_pinned(const void* p) {
 // fp64 is DMA'd in row chunks into two device staging buffers and cast to fp32 by k_cast_in while
 // the next chunk is in flight.
 static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) {
-    if (dtype == PYMFB_F32) {
-        if (c->xps != 0) {             // panel-major X: one strided DMA per column panel
-            const int64_t pw = (int64_t)1 << c->xsh;
-            for (int64_t c0 = 0; c0 < c->n_loc; c0 += pw) {
-                const int64_t w = std::min(pw, c->n_loc - c0);
-                CU(cudaMemcpy2DAsync(c->X_own + (c0 >> c->xsh) * c->xps, c->ldx * sizeof(float), (const float*)host + c0, (size_t)ld * sizeof(float),
-                                     (size_t)w * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
-            }
-        } else if (ld == c->n_loc && c->ldx == c->n_loc)
+    if (dtype == PYMFB_F32 && c->xps == 0) {
+        if (ld == c->n_loc && c->ldx == c->n_loc)
             CU(cudaMemcpyAsync(c->X_own, host, (size_t)c->d * c->n_loc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         else
             CU(cudaMemcpy2DAsync(c->X_own, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float),
                                  (size_t)c->n_loc * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
         return 0;
     }
+    // fp64 (cast) and / or panel-major X (scatter): whole rows travel by DMA into a device staging pair - long
+    // contiguous transfers whatever the device layout is - and one kernel casts / places them
     const int NB = 2;
-    const int64_t row_bytes = c->n_loc * 8;
+    const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
+    const int64_t row_bytes = c->n_loc * (int64_t)esz;
     int64_t rows_per = std::min<int64_t>(c->d, std::max<int64_t>(1, (64LL << 20) / row_bytes));
-    double* dstage[NB] = {nullptr, nullptr};
+    void* dstage[NB] = {nullptr, nullptr};
     cudaEvent_t cast_done[NB] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied = nullptr;
@@ -1149,13 +1152,12 @@ static int pinned_upload(pymfb_ctx* c, const void* host, int dtype, int64_t ld) 
         const int b = (int)(chunk % NB);
         const int64_t nr = std::min(rows_per, c->d - r0);
         if (chunk >= NB) UP(cudaStreamWaitEvent(copy_stream, cast_done[b], 0));   // staging buffer free again
-        UP(cudaMemcpy2DAsync(dstage[b], (size_t)row_bytes, (const char*)host + (size_t)r0 * ld * 8, (size_t)ld * 8,
+        UP(cudaMemcpy2DAsync(dstage[b], (size_t)row_bytes, (const char*)host + (size_t)r0 * ld * esz, (size_t)ld * esz,
                              (size_t)row_bytes, (size_t)nr, cudaMemcpyHostToDevice, copy_stream));
         UP(cudaEventRecord(copied, copy_stream));
         UP(cudaStreamWaitEvent(c->stream, copied, 0));
-        k_cast_in<double><<<grid_for(nr * c->n_loc, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-            dstage[b], c->n_loc, c->X_own + r0 * c->ldx, c->ldx, nr, c->n_loc, 0, c->xps, c->xsh);
-        c->launches += 1;
+        if (dtype == PYMFB_F32) launch_place_x<float>(c, (const float*)dstage[b], c->n_loc, r0, nr, c->n_loc, 0);
+        else launch_place_x<double>(c, (const double*)dstage[b], c->n_loc, r0, nr, c->n_loc, 0);
         UP(cudaGetLastError());
         UP(cudaEventRecord(cast_done[b], c->stream));
     }
@@ -1200,17 +1202,12 @@ int pymfb_upload_x_panel(pymfb_ctx* c, const void* host, int dtype, int64_t ld, 
     if (col0 < 0 || ncols <= 0 || col0 + ncols > c->n_loc || ld < ncols) return fail("bad panel: col0=%lld ncols=%lld ld=%lld n_local=%lld", (long long)col0, (long long)ncols, (long long)ld, (long long)c->n_loc);
     CU(cudaSetDevice(c->device));
     if (!host_is_pinned(host)) c->last_upload_pinned = false;      // the runtime stages pageable panels itself (synchronous)
-    if (dtype == PYMFB_F32) {
-        // split at the panel boundaries of the device layout (one piece when X is row-major)
-        for (int64_t a = col0; a < col0 + ncols;) {
-            const int64_t pend = ((a >> c->xsh) + 1) << c->xsh;
-            const int64_t w = std::min(col0 + ncols, pend) - a;
-            CU(cudaMemcpy2DAsync(c->X_own + xpanel_off(a, c->xps, c->xsh) + a, c->ldx * sizeof(float), (const float*)host + (a - col0),
-                                 (size_t)ld * sizeof(float), (size_t)w * sizeof(float), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
-            a += w;
-        }
-    } else {
-        const size_t need = (size_t)c->d * ncols * sizeof(double);
+    if (dtype == PYMFB_F32 && c->xps == 0) {
+        CU(cudaMemcpy2DAsync(c->X_own + col0, c->ldx * sizeof(float), host, (size_t)ld * sizeof(float), (size_t)ncols * sizeof(float),
+                             (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+    } else {                                   // cast (fp64) and / or scatter into the panel-major layout on the device
+        const size_t esz = dtype == PYMFB_F32 ? 4 : 8;
+        const size_t need = (size_t)c->d * ncols * esz;
         if (need > c->panel_stage_bytes[slot]) {
             CU(cudaStreamSynchronize(c->stream));
             if (c->panel_stage[slot]) CU(cudaFree(c->panel_stage[slot]));
@@ -1218,11 +1215,10 @@ int pymfb_upload_x_panel(pymfb_ctx* c, const void* host, int dtype, int64_t ld, 
             CU(cudaMalloc(&c->panel_stage[slot], need));
             c->panel_stage_bytes[slot] = need;
         }
-        CU(cudaMemcpy2DAsync(c->panel_stage[slot], (size_t)ncols * sizeof(double), host, (size_t)ld * sizeof(double),
-                             (size_t)ncols * sizeof(double), (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
-        k_cast_in<double><<<grid_for(c->d * ncols, 256, 16 * c->sm_count), 256, 0, c->stream>>>(
-            (const double*)c->panel_stage[slot], ncols, c->X_own, c->ldx, c->d, ncols, col0, c->xps, c->xsh);
-        c->launches += 1;
+        CU(cudaMemcpy2DAsync(c->panel_stage[slot], (size_t)ncols * esz, host, (size_t)ld * esz,
+                             (size_t)ncols * esz, (size_t)c->d, cudaMemcpyHostToDevice, c->stream));
+        if (dtype == PYMFB_F32) launch_place_x<float>(c, (const float*)c->panel_stage[slot], ncols, 0, c->d, ncols, col0);
+        else launch_place_x<double>(c, (const double*)c->panel_stage[slot], ncols, 0, c->d, ncols, col0);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(c->panel_ev[slot], c->stream));
