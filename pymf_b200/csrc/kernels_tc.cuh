@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
          int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp,
-         float* __restrict__ Ppart, int64_t part_stride, int xsh) {
+         float* __restrict__ Ppart, int64_t part_stride, int xsh, int xrev) {
     // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
     // Ppart != nullptr: deterministic combine of the column splits - every task stores its sums in copy (task / num_rb)
     // of P's layout (part_stride floats apart) and k_sum_copies adds the copies in split order into P afterwards.
@@ -526,7 +526,9 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
     auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
     auto task_chunks = [&](int task, int& c_begin) {     // number of 32-column stages of a task
-        const int cs = task / num_rb;
+        // xrev: walk the column ranges from the END of the matrix - the H-update pass that ran just before finished
+        // there, so the first tasks find their X columns still in L2 (and this pass ends where the next H-update starts)
+        const int cs = xrev ? (num_tasks / num_rb - 1 - task / num_rb) : task / num_rb;
         c_begin = cs * cols_per_task;
         const int c_end = min(n_loc, c_begin + cols_per_task);
         return (c_end - c_begin + 31) / 32;
@@ -960,11 +962,6 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
             const float xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
-            float hsum = 0.f;
-            if (wmean != nullptr) {
-#pragma unroll
-                for (int j = 0; j < KP; ++j) hsum += hreg[j];
-            }
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
                 if (q == 0) TRACE_AT(g * seg_c, 10);
@@ -994,6 +991,11 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+                float hsum = 0.f;                     // column sum of the old H tile (short-lived: computed where it is used)
+                if (wmean != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) hsum += hreg[j];
+                }
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
                     float dh[16], dl[16];
@@ -1024,8 +1026,13 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                             const float h = hreg[j0 + j];
                             float cj = creg[j0 + j], dj = dh[j] + dl[j];
                             if (wmean != nullptr) {
+#if defined(PYMFB_MEAN_LDG)
+                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
+                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+#else
                                 cj = fmaf(s_mean[j0 + j], xs, cj);
                                 dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
+#endif
                             }
                             const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
@@ -1061,7 +1068,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
          const __grid_constant__ CUtensorMap mapHA, const DevState* __restrict__ st,
          float* __restrict__ PA, float* __restrict__ PB, int d, int n_loc,
          int cols_per_task, int num_rb, int x_tasks, int hh_cols_per_task, int num_tasks,
-         float* __restrict__ dbg, float* __restrict__ PpartA, float* __restrict__ PpartB, int xsh) {
+         float* __restrict__ dbg, float* __restrict__ PpartA, float* __restrict__ PpartB, int xsh, int xrev) {
     // PpartA != nullptr: deterministic combine of the column splits (see k_xht_tc): copies of A are d * KP floats
     // apart, copies of B = H H^T (one per H H^T task) KP * KP floats; k_sum_copies then writes P.
     using Cfg = TsCfg<KP>;
@@ -1101,7 +1108,7 @@ k_xht_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         hh = task >= x_tasks;
         int cpt, cs;
         if (hh) { cs = task - x_tasks; cpt = hh_cols_per_task; row0 = 0; }
-        else { cs = task / num_rb; cpt = cols_per_task; row0 = (task % num_rb) * 128; }
+        else { cs = xrev ? (x_tasks / num_rb - 1 - task / num_rb) : task / num_rb; cpt = cols_per_task; row0 = (task % num_rb) * 128; }   // xrev: see k_xht_tc
         c_begin = cs * cpt;
         const int c_end = min(n_loc, c_begin + cpt);
         return (c_end - c_begin + 31) / 32;
@@ -1425,6 +1432,7 @@ struct TcPlan {
     float* wmean = nullptr;    // kp column means of W, kp column means of G, CM_SPLITS x kp partials
     float* gmean = nullptr;
     float* cm_part = nullptr;
+    int xrev = 1;              // X H^T pass walks the column ranges backwards (L2 reuse across the pass boundary)
     int seg_c = 1;             // stages per segment of the W^T X contraction (= kp / 32: the G H chain length)
     float lam_h = 0.f;         // BNMF penalty weight of the next H-update launch (0 = plain NMF), set by the scheduler
     std::string err;
@@ -1610,6 +1618,7 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     }
 #endif
     p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
+    { const char* e = getenv("PYMFB_XREV"); p.xrev = (e && e[0] == '0') ? 0 : 1; }
     {   // Bias of the H-update ratio C / D (see "Segments"): the TS kernels (k <= 64) contract against centered
         // operands and keep SEG_STAGES-stage segments; the SS kernels give the C chain the D chain's length.
         // PYMFB_SEG_C / PYMFB_CENTER override both for experiments.
@@ -1729,7 +1738,7 @@ inline void ts_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     const int grid = std::min(ntasks, p.sm_count);
     tc::k_xht_ts<KP><<<grid, tc::X_THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_x, p.mapH_x[hsrc], p.mapH_a[hsrc], st, P, P + p.d * p.kp, (int)p.d, (int)p.n_loc, p.x_cols_per_task,
-        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg, p.xpart, p.xpartB, p.xsh);
+        p.x_rb, p.x_tasks, p.hh_cols_per_task, ntasks, p.dbg, p.xpart, p.xpartB, p.xsh, p.xrev);
 }
 inline int tc_h_update(TcPlan& p, const DevState* st, const float* Hc, float* Hn, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
@@ -1755,7 +1764,7 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
-            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh);
+            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh, p.xrev);
 }
 // true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
 // extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
@@ -1769,7 +1778,7 @@ inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cu
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
-            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel);
+            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel, 0);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;

@@ -274,11 +274,6 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
             const float xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
-            float hsum = 0.f;
-            if (wmean != nullptr) {
-#pragma unroll
-                for (int j = 0; j < KP; ++j) hsum += hreg[j];
-            }
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
                 if (q == 0) TRACE_AT(g * seg_c, 10);
@@ -308,6 +303,11 @@ k_h_update_ts2(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+                float hsum = 0.f;                     // column sum of the old H tile (short-lived: computed where it is used)
+                if (wmean != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) hsum += hreg[j];
+                }
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
                     float dh[16], dl[16];
