@@ -16,7 +16,7 @@ for f in sys.argv[1:]:
         r.get("frac", 0), r.get("hbm_frac", 0), r.get("tensor_frac", 0), c.get("sm_mhz"), c.get("reasons"), j.get("gpu_launches")))
     for k in ("e2e", "e2e_pageable"):
         e = j.get(k)
-        if e:
+        if e and "seconds_total" in e:
             print("  %-13s %.3f it/s  total %.3f s (upload %.3f, iterate %.3f)%s" % (
                 k, e["value"], e["seconds_total"], e.get("seconds_upload") or 0, e.get("seconds_iterations") or 0,
                 ("  ratio_to_pinned %.2f" % e["ratio_to_pinned"]) if "ratio_to_pinned" in e else ""))

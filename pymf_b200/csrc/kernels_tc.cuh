@@ -35,8 +35,10 @@
 #include "common.cuh"
 
 #ifndef PYMFB_TC_RAW_HI
-#define PYMFB_TC_RAW_HI 0   // 1: feed the raw fp32 tile as the hi operand (relies on the MMA ignoring
-                            //    the low 13 mantissa bits); 0: write the masked hi tile back explicitly
+#define PYMFB_TC_RAW_HI 1   // 1: feed the raw fp32 tile as the hi operand - tcgen05.mma.kind::tf32 ignores the low 13
+                            //    mantissa bits, bit-identical to the masked tile (tests/_rawhi_check.py) and 16 KB less
+                            //    shared-memory traffic per stage: cfg3 49.99 -> 48.85 ms per iteration, same box;
+                            //    0: write the masked hi tile back explicitly
 #endif
 
 namespace pymfb {
@@ -114,6 +116,11 @@ constexpr int kNoPanel = 31;
 __device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, int xsh) {
     const int p = col >> xsh;
     tma_load_3d(dst, map, bar, col - (p << xsh), row, p);
+}
+// L2 prefetch of a box of X (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_x(const CUtensorMap* map, int col, int row, int xsh) {
+    const int p = col >> xsh;
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(col - (p << xsh)), "r"(row), "r"(p) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -197,7 +204,12 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 // split `nvec` float4 of a stage buffer: raw -> (hi in place unless RAW_HI) + lo buffer
+// One element group at a time (load, split, store).  Issuing all eight loads of a thread before its first store
+// (-DPYMFB_SPLIT_BATCHED: the split warps then no longer expose a shared-memory round trip per group) was measured
+// SLOWER on the k = 128 kernels, cfg3 49.9 -> 51.8 ms per iteration on the same box: the bursts of loads compete
+// with the MMA's operand reads for the shared-memory port, which is what bounds these kernels.
 __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, int tid, int nthreads) {
+#if !defined(PYMFB_SPLIT_BATCHED)
     for (int i = tid; i < nvec; i += nthreads) {
         float4 v = raw[i], h, l;
         split4(v, h, l);
@@ -206,6 +218,23 @@ __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, 
 #endif
         lo[i] = l;
     }
+#else
+    constexpr int B = 8;                               // XSTAGE_BYTES / 16 / 128 threads
+    for (int i0 = tid; i0 < nvec; i0 += B * nthreads) {
+        float4 v[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) if (i0 + b * nthreads < nvec) v[b] = raw[i0 + b * nthreads];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (i0 + b * nthreads < nvec) {
+                float4 h, l;
+                split4(v[b], h, l);
+                raw[i0 + b * nthreads] = h;
+                lo[i0 + b * nthreads] = l;
+            }
+        }
+    }
+#endif
 }
 
 // [H_hi ; H_lo] companion of H ("Hs", the B operand of the X.H^T pass) is stored CHUNK-MAJOR:
@@ -266,7 +295,8 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
-              int kh_rows, int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn, int xsh) {
+              int kh_rows, int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn, int xsh, int pf) {
+    // pf: L2 prefetch distance of X in stages (0 = off)
     // xsh: log2 of the panel width of X (tma_load_x)
     // seg_c: stages per accumulation segment of the W^T X contraction (see "Segments" above)
     // kh_rows: rows of H contracted for G H (= the padded k of the whole problem).  For k <= 128 it equals KP;
@@ -323,6 +353,10 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) tma_load_x(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0, xphase ? xsh : kNoPanel);
+                        if (pf > 0 && it + pf < nd) {      // pull the rows this tile needs pf stages from now into L2
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) tma_prefetch_x(&mapX, col0 + 32 * c, (it + pf) * R1, xsh);
+                        }
 #pragma unroll
                         for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
                     }
@@ -490,7 +524,7 @@ __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
          int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp,
-         float* __restrict__ Ppart, int64_t part_stride, int xsh, int xrev) {
+         float* __restrict__ Ppart, int64_t part_stride, int xsh, int xrev, int pf) {
     // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
     // Ppart != nullptr: deterministic combine of the column splits - every task stores its sums in copy (task / num_rb)
     // of P's layout (part_stride floats apart) and k_sum_copies adds the copies in split order into P afterwards.
@@ -547,6 +581,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
                         tma_load_x(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0, xsh);
+                        if (pf > 0 && ch + pf < nch) tma_prefetch_x(&mapX, c_begin + 32 * (ch + pf), row0, xsh);
                         tma_load_2d(hch(s), &mapH, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));   // [H_hi ; H_lo] chunk
                     }
                     __syncwarp();
@@ -1432,7 +1467,9 @@ struct TcPlan {
     float* wmean = nullptr;    // kp column means of W, kp column means of G, CM_SPLITS x kp partials
     float* gmean = nullptr;
     float* cm_part = nullptr;
-    int xrev = 1;              // X H^T pass walks the column ranges backwards (L2 reuse across the pass boundary)
+    int ss_pf = 0;             // SS kernels: L2 prefetch distance of X in stages (PYMFB_SS_PF)
+    int xrev = 0;              // experiment (PYMFB_XREV=1): the X H^T pass walks the column ranges backwards, hoping to find the
+                               // tail of the H-update pass in L2 - measured neutral on cfg2 / cfg3 / cfg4 k=64, so off
     int seg_c = 1;             // stages per segment of the W^T X contraction (= kp / 32: the G H chain length)
     float lam_h = 0.f;         // BNMF penalty weight of the next H-update launch (0 = plain NMF), set by the scheduler
     std::string err;
@@ -1618,7 +1655,8 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     }
 #endif
     p.h_tiles = (int)((n_loc + tc::TILE_COLS - 1) / tc::TILE_COLS);
-    { const char* e = getenv("PYMFB_XREV"); p.xrev = (e && e[0] == '0') ? 0 : 1; }
+    { const char* e = getenv("PYMFB_XREV"); p.xrev = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("PYMFB_SS_PF"); p.ss_pf = e ? std::max(0, atoi(e)) : 0; }
     {   // Bias of the H-update ratio C / D (see "Segments"): the TS kernels (k <= 64) contract against centered
         // operands and keep SEG_STAGES-stage segments; the SS kernels give the C chain the D chain's length.
         // PYMFB_SEG_C / PYMFB_CENTER override both for experiments.
@@ -1717,7 +1755,7 @@ inline void tc_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
         tc::k_h_update_tc<KP><<<grid, tc::HCfg<KP>::THREADS, tc::HCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_h, p.mapW_b[b], p.mapH_h[hsrc], p.mapG_b[b], st, p.Hbuf[hsrc] + hoff, Hn + hoff, p.Hs[hsrc ^ 1] + 2 * hoff,
             p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.kp, p.seg_c, p.lam_h,
-            p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr, p.xsh);
+            p.Dp ? p.Dp + hoff : nullptr, p.Dn ? p.Dn + hoff : nullptr, p.xsh, p.ss_pf);
     }
 }
 // experiment knob: PYMFB_GRID caps the CTA count of the H-update kernels (per-SM pipeline capacity measurements)
@@ -1764,7 +1802,7 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
-            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh, p.xrev);
+            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh, p.xrev, p.ss_pf);
 }
 // true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
 // extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
@@ -1778,7 +1816,7 @@ inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cu
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
-            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel, 0);
+            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel, 0, 0);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
