@@ -184,13 +184,17 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy);
+__device__ __forceinline__ void tma_prefetch_2d_hint(const CUtensorMap* map, int c0, int c1, uint64_t policy);
 __device__ __forceinline__ void tma_load_x_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, int xsh, uint64_t policy) {
+    if (xsh == kNoPanel) { tma_load_2d_hint(dst, map, bar, col, row, policy); return; }
     const int pn = col >> xsh;
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(dst), "l"(map), "r"(bar), "r"(col - (pn << xsh)), "r"(row), "r"(pn), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_x_hint(const CUtensorMap* map, int col, int row, int xsh, uint64_t policy) {
+    if (xsh == kNoPanel) { tma_prefetch_2d_hint(map, col, row, policy); return; }
     const int pn = col >> xsh;
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.L2::cache_hint [%0, {%1, %2, %3}], %4;" ::"l"(map), "r"(col - (pn << xsh)), "r"(row), "r"(pn), "l"(policy) : "memory");
 }

@@ -272,14 +272,15 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t ldx, int64_t rows,
            const float* __restrict__ H, int64_t ldh, int64_t n_loc, int64_t cols_per_split,
            float* __restrict__ P, int64_t ldp, int nrb_x, int64_t rows_h, float* __restrict__ PB,
-           float* __restrict__ Ppart, int64_t part_stride, unsigned* __restrict__ tickets,
+           float* __restrict__ Ppart, int64_t part_stride,
            int64_t xps = 0, int xsh = kNoPanelShift) {
     // Row blocks [0, nrb_x) of the grid compute X H^T; when PB != nullptr the remaining row blocks compute H H^T in
     // the same launch (the streamed operand is then H itself, rows_h rows, output PB) - one launch instead of two.
-    // Column splits (gridDim.y) are combined DETERMINISTICALLY when Ppart != nullptr: every split parks its block in
-    // copy blockIdx.y of the [A | B] layout (part_stride floats apart), and the split that arrives last on the
-    // block's ticket sums the copies in split order and overwrites P (no clearing, no atomics: W is bit-reproducible
-    // from run to run).  Ppart == nullptr: fp32 atomics into a cleared P.
+    // Column splits (gridDim.y) are combined DETERMINISTICALLY when Ppart != nullptr: every split stores its block in
+    // copy blockIdx.y of the [A | B] layout (part_stride floats apart) and k_sum_copies adds the copies in split
+    // order into P afterwards (no clearing, no atomics: W is bit-reproducible from run to run; an in-kernel
+    // "last arrival sums" variant cost cfg1 8.7 us per iteration in fences and ticket round trips).
+    // Ppart == nullptr: fp32 atomics into a cleared P.
     if (st->stop) return;
     const int64_t out_off = ((int)blockIdx.x >= nrb_x) ? (PB - P) : 0;
     if ((int)blockIdx.x >= nrb_x) { X = H; ldx = ldh; rows = rows_h; P = PB; xps = 0; xsh = kNoPanelShift; }
@@ -356,50 +357,15 @@ k_xht_simt(const DevState* __restrict__ st, const float* __restrict__ X, int64_t
         }
         return;
     }
-    const int ns = (int)gridDim.y;
-    if (ns > 1) {
-        float* part = Ppart + (int64_t)blockIdx.y * part_stride + out_off;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t r = row0 + tr + 32 * i;
-            if (r < rows) {
-#pragma unroll
-                for (int j = 0; j < TK; ++j) part[r * ldp + kb0 + tk * TK + j] = acc[i][j];
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        __shared__ bool last;
-        if (tid == 0) {
-            unsigned* tk_ = tickets + (int64_t)blockIdx.x * gridDim.z + blockIdx.z;
-            last = atomicAdd(tk_, 1u) == (unsigned)(ns - 1);
-            if (last) *tk_ = 0u;                   // ready for the next launch
-        }
-        __syncthreads();
-        if (!last) return;
-        __threadfence();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < TK; ++j) acc[i][j] = 0.f;
-        for (int sp = 0; sp < ns; ++sp) {
-            const float* part_s = Ppart + (int64_t)sp * part_stride + out_off;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = row0 + tr + 32 * i;
-                if (r < rows) {
-#pragma unroll
-                    for (int j = 0; j < TK; ++j) acc[i][j] += __ldcg(part_s + r * ldp + kb0 + tk * TK + j);
-                }
-            }
-        }
-    }
+    // deterministic mode: this split's block goes into its own copy of the [A | B] layout (or straight into P when
+    // there is only one split); k_sum_copies then adds the copies in split order
+    float* dst = ((int)gridDim.y > 1) ? Ppart + (int64_t)blockIdx.y * part_stride + out_off : P;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t r = row0 + tr + 32 * i;
         if (r < rows) {
 #pragma unroll
-            for (int j = 0; j < TK; ++j) P[r * ldp + kb0 + tk * TK + j] = acc[i][j];
+            for (int j = 0; j < TK; ++j) dst[r * ldp + kb0 + tk * TK + j] = acc[i][j];
         }
     }
 }

@@ -114,11 +114,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // see "Layout of the data matrix" in common.cuh; xsh = log2(panel width), kNoPanel for a single panel.
 constexpr int kNoPanel = 31;
 __device__ __forceinline__ void tma_load_x(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, int xsh) {
+    if (xsh == kNoPanel) { tma_load_2d(dst, map, bar, col, row); return; }    // row-major matrices keep 2-D maps (make_map3)
     const int p = col >> xsh;
     tma_load_3d(dst, map, bar, col - (p << xsh), row, p);
 }
 // L2 prefetch of a box of X (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_x(const CUtensorMap* map, int col, int row, int xsh) {
+    if (xsh == kNoPanel) { asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(col), "r"(row) : "memory"); return; }
     const int p = col >> xsh;
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(col - (p << xsh)), "r"(row), "r"(p) : "memory");
 }
@@ -819,9 +821,16 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
     // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
     // as H, written by k_gh_posneg_simt) instead of the G H accumulator
+#if !defined(PYMFB_TS_NO_CENTER)
     __shared__ float s_mean[2 * KP];          // [w_mean | g_mean]: read on the critical tail of every tile, so not from global
     if (threadIdx.x < 2 * KP)
         s_mean[threadIdx.x] = (wmean == nullptr) ? 0.f : (threadIdx.x < KP ? wmean[threadIdx.x] : gmean[threadIdx.x - KP]);
+#endif
+#if defined(PYMFB_TS_SEG_CONST)
+    constexpr int segc = SEG_STAGES;          // A/B builds: compile-time segment length as in round 1
+#else
+    const int segc = seg_c;
+#endif
     using Cfg = TsCfg<KP>;
     if (st->stop) return;
     extern __shared__ uint8_t smem_raw[];
@@ -900,7 +909,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
-                    const int seg_end = (it < nd) ? min(it + seg_c, nd) : nit;
+                    const int seg_end = (it < nd) ? min(it + segc, nd) : nit;
                     const uint32_t b = g & 1u;
                     TRACE_AT(mc, 8);
                     mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
@@ -983,7 +992,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
         }
     } else {
         const int q = warp & 3;
-        const int nsegC = (nd + seg_c - 1) / seg_c;
+        const int nsegC = (nd + segc - 1) / segc;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -993,15 +1002,30 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             // Old H of this lane's column, fetched NOW: under a saturated memory system a dependent
             // global load takes ~3 us, and doing it after the last segment stalled every tile by ~10 us.
             const int col = tile * TILE_COLS + q * 32 + lane;
-            float hreg[KP];
+            // KP = 64 sits at the register cap of this kernel (168): holding the old H column (64 values) next to
+            // the 64 sums through the whole tile made the compiler spill and cost the pass 20 % once the centering
+            // terms were added (same-box bisect).  LEAN: the column is pulled into L2 when the last W^T X segment
+            // starts, summed (and thereby pulled into L1) while the G H MMAs are in flight, and re-read 16 values at a time.
+            constexpr bool LEAN = (KP == 64);
+            float hreg[LEAN ? 1 : KP];
+            float xs = 0.f;
+            if constexpr (!LEAN) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
-            const float xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+                for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
+                xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+            }
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
+                if constexpr (LEAN) {
+                    if (seg == nsegC - 1 && col < n_loc) {
+#pragma unroll 8
+                        for (int j = 0; j < KP; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(Hc + (int64_t)j * ldh + col));
+                        if (wmean != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(xsum + col));
+                    }
+                }
                 const uint32_t b = g & 1u;
-                if (q == 0) TRACE_AT(g * seg_c, 10);
+                if (q == 0) TRACE_AT(g * segc, 10);
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
-                if (q == 0) TRACE_AT(g * seg_c, 11);
+                if (q == 0) TRACE_AT(g * segc, 11);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
 #pragma unroll
@@ -1018,19 +1042,27 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (q == 0) TRACE_AT(g * seg_c, 12);
+                if (q == 0) TRACE_AT(g * segc, 12);
                 if (lane == 0) mbar_arrive(tempty_bar(b));
             }
             {
+                float hsum = 0.f;                     // column sum of the old H tile (for the centered G H)
+                if constexpr (LEAN) {
+                    if (col < n_loc) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += __ldg(Hc + (int64_t)j * ldh + col);
+                        if (wmean != nullptr) xs = __ldg(xsum + col);
+                    }
+                } else {
+                    if (wmean != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += hreg[j];
+                    }
+                }
                 const uint32_t b = g & 1u;
                 mbar_wait(tfull_bar(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
-                float hsum = 0.f;                     // column sum of the old H tile (short-lived: computed where it is used)
-                if (wmean != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) hsum += hreg[j];
-                }
 #pragma unroll
                 for (int j0 = 0; j0 < KP; j0 += 16) {
                     float dh[16], dl[16];
@@ -1058,8 +1090,10 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int64_t o = (int64_t)(j0 + j) * ldh + col;
-                            const float h = hreg[j0 + j];
+                            float h;
+                            if constexpr (LEAN) h = __ldg(Hc + o); else h = hreg[j0 + j];
                             float cj = creg[j0 + j], dj = dh[j] + dl[j];
+#if !defined(PYMFB_TS_NO_CENTER)
                             if (wmean != nullptr) {
 #if defined(PYMFB_MEAN_LDG)
                                 cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
@@ -1069,6 +1103,7 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                                 dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
 #endif
                             }
+#endif
                             const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
                             const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
                             Hn[o] = hn;                                  // new H
@@ -1521,7 +1556,8 @@ inline bool make_map3(CUtensorMap* m, const float* base, int64_t rows, int64_t c
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUtensorMapSwizzle sw = swz == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swz == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+    // a row-major matrix is one panel: plain 2-D map (tma_load_x issues the 2-D instruction for it)
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, paneled ? 3 : 2, (void*)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled(3-D) failed with code " + std::to_string((int)r); return false; }
     return true;
@@ -1637,6 +1673,8 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
         ok = ok && make_map(&p.mapH_x[i], p.Hs[i], (ldh / 32) * 2 * p.kpb, 32, 32, 2 * p.kpb, false, &p.err);   // [H_hi ; H_lo] chunks as B (block 0)
         ok = ok && make_map3(&p.mapH_a[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, 32, 128, 1, &p.err);        // H as A
     }
+    // (addressing the 128-column panels as one 2-D matrix of (panels * d) rows for this kernel, i.e. the 2-D TMA
+    // instruction instead of the 3-D one, was measured: no difference)
     ok = ok && make_map3(&p.mapX_p, X, d, n_loc, ldx, xps, xsh64, tc::TILE_COLS, tc::R1, 0, &p.err);
     for (int i = 0; i < 2; ++i) ok = ok && make_map3(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, tc::TILE_COLS, tc::R1, 0, &p.err);
     if (!ok) return 1;

@@ -211,7 +211,6 @@ struct pymfb_ctx {
 
     int64_t launches = 0;
     float* xpart_simt = nullptr;          // SIMT X H^T pass: copies of [A | B] for the deterministic combine of the column splits
-    unsigned* xtickets_simt = nullptr;
     bool deterministic_simt = true;       // PYMFB_DETERMINISTIC=0: fp32 atomics
     bool uw_smem_set = false;      // k_update_w's dynamic shared memory attribute raised (k > 1536)
     bool last_upload_pinned = false;
@@ -447,22 +446,23 @@ static int launch_xht(pymfb_ctx* c) {
         // X H^T and H H^T in ONE launch: the row blocks beyond those of X stream H itself
         int64_t cps; unsigned ns;
         xht_splits(c, c->d, &cps, &ns);
-        if (!c->xpart_simt && c->deterministic_simt && ns > 1) {      // ns copies of the [A | B] layout + one ticket per block
-            const int64_t nt = (int64_t)((c->d + 127) / 128 + (c->kp + 127) / 128) * (c->kp / c->kb);
+        if (!c->xpart_simt && c->deterministic_simt && ns > 1)        // ns copies of the [A | B] layout
             CU(cudaMalloc(&c->xpart_simt, (size_t)ns * c->ab_count * sizeof(float)));
-            CU(cudaMalloc(&c->xtickets_simt, (size_t)nt * sizeof(unsigned)));
-            CU(cudaMemsetAsync(c->xtickets_simt, 0, (size_t)nt * sizeof(unsigned), c->stream));
-        }
         const int nrb_x = (int)((c->d + 127) / 128), nrb_h = (c->kp + 127) / 128;
         dim3 grid((unsigned)(nrb_x + nrb_h), ns, (unsigned)(c->kp / c->kb));
         float* PB = c->P + c->d * c->kp;
         if (c->kb == 16)
             k_xht_simt<16><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
-                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt, c->xps, c->xsh);
+                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xps, c->xsh);
         else
             k_xht_simt<32><<<grid, SIMT_THREADS, 0, c->stream>>>(c->st, c->X, c->ldx, c->d, Hc, c->ldh, c->n_loc, cps, c->P, c->kp,
-                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xtickets_simt, c->xps, c->xsh);
+                                                                 nrb_x, (int64_t)c->kp, PB, c->xpart_simt, c->ab_count, c->xps, c->xsh);
         c->launches += 1;
+        if (c->xpart_simt && ns > 1) {              // deterministic combine of the column splits
+            tc::k_sum_copies<<<grid_for(c->ab_count / 4, 256, 4 * c->sm_count), 256, 0, c->stream>>>(
+                c->st, c->xpart_simt, (int)ns, c->ab_count, c->P, nullptr, 0, 0, nullptr);
+            c->launches += 1;
+        }
         CU(cudaGetLastError());
     }
     CK(timing_end(c, 1, e0, e1));
@@ -768,7 +768,7 @@ int pymfb_destroy(pymfb_ctx* c) {
         for (auto& p : c->ev[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->p_nccl && g_nccl.MemFree) g_nccl.MemFree(c->P); else cudaFree(c->P);
     cudaFree(c->G); cudaFree(c->Gpart); cudaFree(c->red_scratch); cudaFree(c->st);
-    cudaFree(c->h_cpart); cudaFree(c->h_tickets); cudaFree(c->xpart_simt); cudaFree(c->xtickets_simt);
+    cudaFree(c->h_cpart); cudaFree(c->h_tickets); cudaFree(c->xpart_simt);
     cudaFree(c->Gpos); cudaFree(c->Gneg); cudaFree(c->Dp); cudaFree(c->Dn); cudaFree(c->inv_work); cudaFree(c->Binv);
     for (int s_ = 0; s_ < 2; ++s_) { if (c->panel_ev[s_]) cudaEventDestroy(c->panel_ev[s_]); cudaFree(c->panel_stage[s_]); }
     cudaFree(c->stage); cudaFree(c->ferr_dev); cudaFree(c->flush_buf); cudaFree(c->X_own); cudaFree(c->Wt); cudaFree(c->resid_part);
@@ -1443,7 +1443,6 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
     cudaStream_t s = c->stream;
     float *Q = nullptr, *Y = nullptr, *Zt = nullptr, *Zt2 = nullptr, *Rm = nullptr, *Rt = nullptr, *Ct = nullptr, *Ppart = nullptr;
     double *gpart = nullptr, *Tm = nullptr, *work = nullptr, *vals = nullptr, *norms = nullptr;
-    unsigned* tickets = nullptr;
     // X Z^T launches: column splits combined deterministically (k_xht_simt)
     const int64_t rowblocks = (d + 127) / 128, kblocks = b / 32, chunks = (n + XHT_CK - 1) / XHT_CK;
     int64_t want = std::min<int64_t>(chunks, std::max<int64_t>(1, (4LL * c->sm_count) / (rowblocks * kblocks)));
@@ -1457,7 +1456,7 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
     auto cleanup = [&]() {
         cudaStreamSynchronize(s);
         cudaFree(Q); cudaFree(Y); cudaFree(Zt); cudaFree(Zt2); cudaFree(Rm); cudaFree(Rt); cudaFree(Ct); cudaFree(Ppart);
-        cudaFree(gpart); cudaFree(Tm); cudaFree(work); cudaFree(vals); cudaFree(norms); cudaFree(tickets);
+        cudaFree(gpart); cudaFree(Tm); cudaFree(work); cudaFree(vals); cudaFree(norms);
     };
 #define SV(call)                                                                                   \
     do {                                                                                           \
@@ -1476,8 +1475,6 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
     SV(cudaMalloc(&work, (size_t)2 * b * b * 8)); SV(cudaMalloc(&vals, (size_t)b * 8)); SV(cudaMalloc(&norms, (size_t)4 * b * 8));
     // (a non-null Ppart selects k_xht_simt's overwrite mode, also for a single split)
     SV(cudaMalloc(&Ppart, ns > 1 ? (size_t)ns * d * b * 4 : 16));
-    SV(cudaMalloc(&tickets, (size_t)rowblocks * kblocks * sizeof(unsigned)));
-    SV(cudaMemsetAsync(tickets, 0, (size_t)rowblocks * kblocks * sizeof(unsigned), s));
     // G = A^T A (by_rows = 0, A: len x b) or A A^T (by_rows = 1, A: b x len) in fp64 -> Tm
     auto gram = [&](const float* A, int64_t ld, int64_t len, int by_rows) {
         const int sp = by_rows ? gsplit_n : gsplit_d;
@@ -1490,7 +1487,7 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
     // Out (d x b) = A (d x b) * M where Mt = M^T is b x b row-major:  Out[r][i] = sum_j A[r][j] Mt[i][j]
     auto right_mul = [&](const float* A, const float* Mt, float* Out) {
         k_xht_simt<32><<<dim3((unsigned)rowblocks, 1, (unsigned)kblocks), SIMT_THREADS, 0, s>>>(
-            c->st, A, b, d, Mt, b, b, b, Out, b, (int)rowblocks, 0, nullptr, Ppart, 0, tickets);
+            c->st, A, b, d, Mt, b, b, b, Out, b, (int)rowblocks, 0, nullptr, Ppart, 0);
         c->launches += 1;
     };
     // Out (b x n) = L^T In with L b x b row-major (L[j][i]):  Out[i][col] = sum_j L[j][i] In[j][col]
@@ -1521,8 +1518,10 @@ int pymfb_nndsvd(pymfb_ctx* c, int max_iter, double tol, int extra_iter, int* it
         rayleigh_ritz();
         left_mul_t(Rm, b, b, Zt, ldz, Zt2);                      // rows of Zt2: (Ritz vector)^T X
         k_xht_simt<32><<<dim3((unsigned)rowblocks, ns, (unsigned)kblocks), SIMT_THREADS, 0, s>>>(
-            c->st, c->X, c->ldx, d, Zt2, ldz, n, cps, Y, b, (int)rowblocks, 0, nullptr, Ppart, d * b, tickets, c->xps, c->xsh);
-        c->launches += 1;
+            c->st, c->X, c->ldx, d, Zt2, ldz, n, cps, Y, b, (int)rowblocks, 0, nullptr, Ppart, d * b, c->xps, c->xsh);
+        if (ns > 1)
+            tc::k_sum_copies<<<grid_for(d * b / 4, 256, 4 * c->sm_count), 256, 0, s>>>(c->st, Ppart, (int)ns, d * b, Y, nullptr, 0, 0, nullptr);
+        c->launches += 2;
         orthonormalise(Y, Q);                                    // Y = X X^T (Ritz vectors) -> next Q
         SV(cudaGetLastError());
         SV(cudaMemcpyAsync(ev.data(), vals, (size_t)b * 8, cudaMemcpyDeviceToHost, s));
