@@ -210,18 +210,14 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 // (-DPYMFB_SPLIT_BATCHED: the split warps then no longer expose a shared-memory round trip per group) was measured
 // SLOWER on the k = 128 kernels, cfg3 49.9 -> 51.8 ms per iteration on the same box: the bursts of loads compete
 // with the MMA's operand reads for the shared-memory port, which is what bounds these kernels.
-__device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, int tid, int nthreads) {
-#if !defined(PYMFB_SPLIT_BATCHED)
-    for (int i = tid; i < nvec; i += nthreads) {
-        float4 v = raw[i], h, l;
-        split4(v, h, l);
-#if !PYMFB_TC_RAW_HI
-        raw[i] = h;
+#ifndef PYMFB_SPLIT_UNROLL
+#define PYMFB_SPLIT_UNROLL 4
 #endif
-        lo[i] = l;
-    }
-#else
-    constexpr int B = 8;                               // XSTAGE_BYTES / 16 / 128 threads
+__device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, int tid, int nthreads) {
+#if defined(PYMFB_EXP_SS_SKIP_SPLIT)
+    return;
+#endif
+    constexpr int B = PYMFB_SPLIT_UNROLL;              // loads in flight per thread (8 = the whole share of a thread)
     for (int i0 = tid; i0 < nvec; i0 += B * nthreads) {
         float4 v[B];
 #pragma unroll
@@ -231,12 +227,13 @@ __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, 
             if (i0 + b * nthreads < nvec) {
                 float4 h, l;
                 split4(v[b], h, l);
+#if !PYMFB_TC_RAW_HI
                 raw[i0 + b * nthreads] = h;
+#endif
                 lo[i0 + b * nthreads] = l;
             }
         }
     }
-#endif
 }
 
 // [H_hi ; H_lo] companion of H ("Hs", the B operand of the X.H^T pass) is stored CHUNK-MAJOR:
@@ -247,6 +244,19 @@ __device__ __forceinline__ void split_buffer(float4* raw, float4* lo, int nvec, 
 __host__ __device__ __forceinline__ int64_t hs_index(int j, int64_t col, int kp2) {
     return ((col >> 5) * kp2 + j) * 32 + (col & 31);
 }
+
+// PYMFB_TRACE (experiment builds only): CTA 0 records clock64() at the hand-over points of its first
+// TRACE_STAGES pipeline stages into dbg + 1 MB; dumped by tc_release() to $PYMFB_TRACE_FILE.
+#if defined(PYMFB_TRACE)
+constexpr int TRACE_STAGES = 4096;
+#define TRACE_AT(stage_idx, slot)                                                                           \
+    do {                                                                                                    \
+        if (dbg != nullptr && blockIdx.x == 0 && lane == 0 && (stage_idx) < (uint32_t)TRACE_STAGES)                   \
+            reinterpret_cast<long long*>(dbg + (1 << 18))[(size_t)(stage_idx) * 16 + (slot)] = clock64();   \
+    } while (0)
+#else
+#define TRACE_AT(stage_idx, slot) do { } while (0)
+#endif
 
 constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "segments" below)
 
@@ -266,21 +276,99 @@ constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "s
 // chain has exactly as many MMAs as the D chain and the two biases cancel in the ratio to first order;
 // the X H^T and H H^T contractions of the W update (ratio A / (W B)) both use SEG_STAGES-stage
 // segments over column ranges that are multiples of a segment, for the same reason.
+// Rings of the SS kernels (round 2).  Round 1 kept ONE ring whose stage held everything a contraction step needs -
+// the X box, its lo tile and the [b_hi | b_lo] operand chunk: 64 KB per 16 KB of X at k = 128, i.e. 3 stages = 48 KB
+// of X in flight per SM, every byte of it parked for the whole TMA -> split -> MMA lifetime (~4 500 cycles).  Ablation
+// builds (build_exp/ablate.sh: no operand loads / no split / half-width MMAs) each took ~10 % off the pass and all
+// three together 29 %: the pass was bound by bytes in flight / slot lifetime, not by the tensor pipe.  The three
+// buffers have very different lifetimes, so they now live in three rings:
+//   X ring   NX x 16 KB   HBM latency + split + MMA      (the long one: gets the most slots)
+//   lo ring  NL x 16 KB   split + MMA                    (allocated by the split warps, not at TMA issue)
+//   B ring   NW x 2KP x 128 B   L2 latency + MMA         (operand chunk, same for every CTA: an L2 hit)
+#ifndef PYMFB_SS_MMA_ORDER
+#define PYMFB_SS_MMA_ORDER 0   // experiment: 0 = hi (N = 2k) / lo (N = k) MMAs interleaved per k-step, 1 = the stage's hi MMAs first, then its
+                               // lo MMAs, 2 = three N = k MMAs per k-step (no accumulator range shared by MMAs of different width)
+#endif
+#ifndef PYMFB_SS_NW
+#define PYMFB_SS_NW 3
+#endif
+#ifndef PYMFB_SS_NL
+#define PYMFB_SS_NL 0      // 0: 2 slots for k > 96, else 3
+#endif
 template <int KP>
-struct HCfg {   // H-update pass
+struct SsRings {
+    static constexpr int BSTAGE_BYTES = 2 * KP * 128;               // [b_hi | b_lo]: 2KP x 32 fp32
+    static constexpr int NW = PYMFB_SS_NW;
+    static constexpr int NL = PYMFB_SS_NL > 0 ? PYMFB_SS_NL : (KP > 96 ? 2 : 3);
+    static constexpr int NX_RAW = (SMEM_LIMIT - 2048 - NW * BSTAGE_BYTES - NL * XSTAGE_BYTES) / XSTAGE_BYTES;
+    static constexpr int NX = NX_RAW > 8 ? 8 : NX_RAW;
+    static constexpr int LO_OFF = NX * XSTAGE_BYTES;
+    static constexpr int B_OFF = LO_OFF + NL * XSTAGE_BYTES;
+    static constexpr int BAR_OFF = B_OFF + NW * BSTAGE_BYTES;
+    static constexpr int NR = NW;                                   // "stage ready" barriers (see SsBars); must be >= NL and >= NW
+    static constexpr int NBAR = 2 * NX + NR + 4;                    // fullx, done, ready, tfull[2], tempty[2]
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(NX >= 2 && NL >= 2 && NW >= 2, "not enough shared memory for the three rings");
+    static_assert(NR >= NL && NR >= NW && NX >= NR, "barrier ring depths");
+    static_assert(NBAR * 8 + 8 <= 512, "barrier area too small");
+    static_assert(SMEM_BYTES <= SMEM_LIMIT, "rings do not fit");
+};
+
+template <int KP>
+struct HCfg : SsRings<KP> {   // H-update pass
     static constexpr int NCH = 2 * KP / 32;                         // 32-column chunks of [hi | lo]
-    static constexpr int WSTAGE_BYTES = NCH * R1 * 128;             // R1 rows x 2KP fp32
-    static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + WSTAGE_BYTES;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int WSTAGE_BYTES = NCH * R1 * 128;             // R1 rows x 2KP fp32 (= BSTAGE_BYTES)
     static constexpr int SEG_COLS = 2 * KP;                         // [hi | small] per segment buffer
     static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;               // 2 warps per TMEM lane quarter for wide k
     static constexpr int NJ = KP / (EPI_WARPS / 4);                 // basis columns per epilogue thread
     static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
-    static_assert(STAGES >= 2, "not enough shared memory for two stages");
     static_assert(NJ % 16 == 0, "epilogue column split must be a multiple of 16");
+    static_assert(WSTAGE_BYTES == SsRings<KP>::BSTAGE_BYTES, "operand stage size");
+};
+
+// Barriers of the SS kernels.  The MMA warp is the serial resource of these kernels: a PYMFB_TRACE run of the first
+// three-ring version (three waits - operand chunk, X box, lo tile - and three tcgen05.commit per stage, one per ring)
+// showed it spending ~1 250 cycles per stage - 230 waiting, 230 issuing the 8 MMAs, 500 in the three commits and 290
+// in loop bookkeeping - against 768 cycles of tensor work.  Hence ONE wait and ONE commit per stage:
+//   ready[i % NR]  the stage's operands are in place: 4 arrivals of the split warps (lo tile written; they waited for
+//                  the X box, so it implies fullx) + the arrive.expect_tx of the operand-chunk producer + its bytes;
+//   done[i % NX]   tcgen05.commit of the stage's MMAs.  It frees the X slot (the X producer waits NX stages back),
+//                  the lo slot (the split warps wait NL stages back) and the chunk slot (NW stages back) alike: MMAs
+//                  complete in order, and a waiter that lags L <= NX stages behind sees at most one completion it does
+//                  not expect on its barrier, so the parity wait cannot alias.
+template <class Cfg>
+struct SsBars {
+    uint32_t base;
+    __device__ __forceinline__ uint32_t fullx(int s) const { return base + 8u * s; }
+    __device__ __forceinline__ uint32_t done(int s) const { return base + 8u * (Cfg::NX + s); }
+    __device__ __forceinline__ uint32_t ready(int s) const { return base + 8u * (2 * Cfg::NX + s); }
+    __device__ __forceinline__ uint32_t tfull(int a) const { return base + 8u * (2 * Cfg::NX + Cfg::NR + a); }
+    __device__ __forceinline__ uint32_t tempty(int a) const { return base + 8u * (2 * Cfg::NX + Cfg::NR + 2 + a); }
+    __device__ __forceinline__ uint32_t tmem_slot() const { return base + 8u * Cfg::NBAR; }
+    __device__ __forceinline__ void init(int epi_warps) const {
+        for (int s = 0; s < Cfg::NX; ++s) { mbar_init(fullx(s), 1); mbar_init(done(s), 1); }
+        for (int s = 0; s < Cfg::NR; ++s) mbar_init(ready(s), 5);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), epi_warps); }
+    }
+};
+// slot index + phase of one ring
+template <int N>
+struct RingPos {
+    int s = 0; uint32_t ph = 0;
+    __device__ __forceinline__ void next() { if (++s == N) { s = 0; ph ^= 1u; } }
+};
+// position in the done[] ring that trails the caller by LAG stages: wait() returns once the MMAs of stage i - LAG have
+// completed (no-op for the first LAG stages); call it once per stage
+template <int NX, int LAG>
+struct DoneLag {
+    RingPos<NX> p; int skip = LAG;
+    template <class Bars>
+    __device__ __forceinline__ void wait(const Bars& bar, bool mine = true) {
+        if (skip > 0) { --skip; return; }
+        if (mine) mbar_wait(bar.done(p.s), p.ph);
+        p.next();
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -288,8 +376,9 @@ struct HCfg {   // H-update pass
 //   C segments:  [ X^T W_hi | X^T W_lo + X_lo^T W_hi ]  over 256-row slices of X  -> summed in registers
 //   D segment :  [ H^T G_hi | H^T G_lo + H_lo^T G_hi ]  over the kp rows of H
 //   epilogue  :  Hn = H * C / (D + 1e-9)
-// X/W and H/G stages travel through the same TMA -> split -> MMA ring.
-// warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: hi/lo split, warps 6..: epilogue.
+// X/W and H/G stages travel through the same TMA -> split -> MMA rings.
+// warp 0: TMA producer of X, warps 1-2: TMA producers of the operand chunks, warp 3: MMA issuer,
+// warps 4-7: lo split, warps 8..: epilogue.
 // ---------------------------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(HCfg<KP>::THREADS, 1)
@@ -309,24 +398,16 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-    // barriers: full[S], ready[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base slot
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto ready_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES + 4));
+    const SsBars<Cfg> bar{smem_base + Cfg::BAR_OFF};
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFF + 8 * Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        bar.init(Cfg::EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(bar.tmem_slot(), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -334,82 +415,134 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 
     const int nd = (d + R1 - 1) / R1;            // stages over the rows of X
     const int nit = nd + kh_rows / R1;           // + stages over the rows of H (for G H)
-    auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
-    auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
+    auto xraw = [&](int s) { return smem_base + s * XSTAGE_BYTES; };
+    auto xlo = [&](int s) { return smem_base + Cfg::LO_OFF + s * XSTAGE_BYTES; };
+    auto wch = [&](int s) { return smem_base + Cfg::B_OFF + s * Cfg::WSTAGE_BYTES; };
 
-    if (warp < NPROD) {
-        // ===== TMA producer =====
-        {
-            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int col0 = tile * TILE_COLS;
-                for (int it = 0; it < nit; ++it) {
-                    if (pcnt++ % NPROD == (uint32_t)warp) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+    if (warp == 0) {
+        // ===== TMA producer of the X / H boxes =====
+        RingPos<Cfg::NX> rx;
+        uint32_t tc_ = 0; (void)tc_;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int col0 = tile * TILE_COLS;
+            for (int it = 0; it < nit; ++it, ++tc_) {
+                TRACE_AT(tc_, 0);
+                mbar_wait(bar.done(rx.s), rx.ph ^ 1);
+                TRACE_AT(tc_, 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar.fullx(rx.s), XSTAGE_BYTES);
+                    const bool xphase = it < nd;
+                    const int r0 = (xphase ? it : it - nd) * R1;
+                    const CUtensorMap* ma = xphase ? &mapX : &mapH;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tma_load_x(xraw(rx.s) + c * (R1 * 128), ma, bar.fullx(rx.s), col0 + 32 * c, r0, xphase ? xsh : kNoPanel);
+                    if (pf > 0 && it + pf < nd) {      // pull the rows this tile needs pf stages from now into L2
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) tma_prefetch_x(&mapX, col0 + 32 * c, (it + pf) * R1, xsh);
+                    }
+                }
+                __syncwarp();
+                rx.next();
+            }
+        }
+    } else if (warp < NPROD) {
+        // ===== TMA producers of the [W_hi|W_lo] / [G_hi|G_lo] chunks (stages alternate between the warps) =====
+        RingPos<Cfg::NW> rw;                        // chunk slot = ready barrier of the stage (NR == NW)
+        DoneLag<Cfg::NX, Cfg::NW> lag;
+        uint32_t cnt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; it < nit; ++it) {
+                const bool mine = cnt++ % (NPROD - 1) == (uint32_t)(warp - 1);
+                if (mine) TRACE_AT(cnt - 1, 10);
+                lag.wait(bar, mine);
+                if (mine) {
+                    TRACE_AT(cnt - 1, 11);
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::WSTAGE_BYTES);
+#if defined(PYMFB_EXP_SS_SKIP_B)
+                        mbar_arrive(bar.ready(rw.s));
+#else
+                        mbar_expect_tx(bar.ready(rw.s), Cfg::WSTAGE_BYTES);
                         const bool xphase = it < nd;
                         const int r0 = (xphase ? it : it - nd) * R1;
-                        const CUtensorMap* ma = xphase ? &mapX : &mapH;
                         const CUtensorMap* mb = xphase ? &mapW : &mapG;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_x(xraw(s) + c * (R1 * 128), ma, full_bar(s), col0 + 32 * c, r0, xphase ? xsh : kNoPanel);
-                        if (pf > 0 && it + pf < nd) {      // pull the rows this tile needs pf stages from now into L2
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) tma_prefetch_x(&mapX, col0 + 32 * c, (it + pf) * R1, xsh);
-                        }
-#pragma unroll
-                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(rw.s) + c * (R1 * 128), mb, bar.ready(rw.s), 32 * c, r0);
+#endif
                     }
                     __syncwarp();
-                    }
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
+                rw.next();
             }
         }
     } else if (warp == NPROD) {
         // ===== MMA issuer =====
         {
+#if defined(PYMFB_EXP_SS_HALF_N)
+            constexpr uint32_t idesc_hl = make_idesc(128, KP, 1, 1);
+            constexpr uint32_t idesc_h = make_idesc(128, KP / 2, 1, 1);
+#else
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 1, 1);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 1, 1);
-            int s = 0; uint32_t ph = 0; uint32_t g = 0;
-            // descriptors of stage 0 (one MMA, K = 8, = two 4-row swizzle atoms, SBO = 512 B; 32-column chunks LBO apart);
-            // stage s / k-group kg add (s * STAGE_BYTES + kg * 1024) >> 4 to the low words, the high words never change
+#endif
+            RingPos<Cfg::NX> rx; RingPos<Cfg::NL> rl; RingPos<Cfg::NW> rw;
+            uint32_t g = 0, mc = 0; (void)mc;
+            // descriptors of slot 0 of each ring (one MMA, K = 8, = two 4-row swizzle atoms, SBO = 512 B; 32-column chunks LBO
+            // apart); slot s / k-group kg add (s * slot bytes + kg * 1024) >> 4 to the low words, the high words never change
+            // (shared-memory addresses are < 2^18, so the 14-bit address field never carries)
             const uint64_t d_hi0 = make_desc(xraw(0), R1 * 128, 512, 1), d_lo0 = make_desc(xlo(0), R1 * 128, 512, 1);
             const uint64_t d_b0 = make_desc(wch(0), R1 * 128, 512, 1);
             const uint32_t dh = (uint32_t)(d_hi0 >> 32);      // identical for the three operands (same LBO / SBO / layout)
             const uint32_t ahi0 = (uint32_t)d_hi0, alo0 = (uint32_t)d_lo0, b0 = (uint32_t)d_b0;
-            uint32_t soff = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int it = 0;
                 while (it < nit) {
                     const int seg_end = (it < nd) ? min(it + seg_c, nd) : nit;
                     const uint32_t b = g & 1u;
-                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar.tempty(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
                     bool first = true;
-                    for (; it < seg_end; ++it) {
-                        mbar_wait(full_bar(s), ph);
-                        mbar_wait(ready_bar(s), ph);
+                    for (; it < seg_end; ++it, ++mc) {
+                        TRACE_AT(mc, 5);
+                        mbar_wait(bar.ready(rw.s), rw.ph);
+                        TRACE_AT(mc, 6);
                         tc_fence_after();
                         if (elect_one()) {
+                            const uint32_t ox = ahi0 + rx.s * (XSTAGE_BYTES >> 4), ol = alo0 + rl.s * (XSTAGE_BYTES >> 4);
+                            const uint32_t ob = b0 + rw.s * (Cfg::WSTAGE_BYTES >> 4);
+#if PYMFB_SS_MMA_ORDER == 0
 #pragma unroll
                             for (int kg = 0; kg < R1 / 8; ++kg) {
-                                const uint32_t o = soff + kg * (1024 >> 4);
-                                umma_tf32_lh(dcol, ahi0 + o, dh, b0 + o, dh, idesc_hl, (first && kg == 0) ? 0u : 1u);
-                                umma_tf32_lh(dcol + KP, alo0 + o, dh, b0 + o, dh, idesc_h, 1u);
+                                const uint32_t o = kg * (1024 >> 4);
+                                umma_tf32_lh(dcol, ox + o, dh, ob + o, dh, idesc_hl, (first && kg == 0) ? 0u : 1u);
+                                umma_tf32_lh(dcol + KP, ol + o, dh, ob + o, dh, idesc_h, 1u);
                             }
-                            umma_commit(empty_bar(s));
+#elif PYMFB_SS_MMA_ORDER == 1
+#pragma unroll
+                            for (int kg = 0; kg < R1 / 8; ++kg)
+                                umma_tf32_lh(dcol, ox + kg * (1024 >> 4), dh, ob + kg * (1024 >> 4), dh, idesc_hl, (first && kg == 0) ? 0u : 1u);
+#pragma unroll
+                            for (int kg = 0; kg < R1 / 8; ++kg)
+                                umma_tf32_lh(dcol + KP, ol + kg * (1024 >> 4), dh, ob + kg * (1024 >> 4), dh, idesc_h, 1u);
+#else
+#pragma unroll
+                            for (int kg = 0; kg < R1 / 8; ++kg) {
+                                const uint32_t o = kg * (1024 >> 4);
+                                const uint32_t acc = (first && kg == 0) ? 0u : 1u;
+                                umma_tf32_lh(dcol, ox + o, dh, ob + o, dh, idesc_h, acc);
+                                umma_tf32_lh(dcol + KP, ox + o, dh, ob + o + ((KP / 32) * R1 * 128 >> 4), dh, idesc_h, acc);
+                                umma_tf32_lh(dcol + KP, ol + o, dh, ob + o, dh, idesc_h, 1u);
+                            }
+#endif
+                            TRACE_AT(mc, 14);
+                            umma_commit(bar.done(rx.s));
+                            if (it + 1 == seg_end) umma_commit(bar.tfull(b));     // last stage of the segment: hand it to the epilogue
                         }
                         __syncwarp();
+                        TRACE_AT(mc, 7);
                         first = false;
-                        soff += Cfg::STAGE_BYTES >> 4;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
+                        rx.next(); rl.next(); rw.next();
                     }
-                    if (elect_one()) umma_commit(tfull_bar(b));
-                    __syncwarp();
                     ++g;
                 }
             }
@@ -417,17 +550,24 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     } else if (warp < NPROD + 5) {
         // ===== split warps: lo tiles (and masked hi) of the X / H operand =====
         const int tid_s = threadIdx.x - 32 * (NPROD + 1);
-        int s = 0; uint32_t ph = 0;
+        RingPos<Cfg::NX> rx; RingPos<Cfg::NL> rl; RingPos<Cfg::NR> rr;
+        DoneLag<Cfg::NX, Cfg::NL> lag;
+        uint32_t sc = 0; (void)sc;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int it = 0; it < nit; ++it) {
-                mbar_wait(full_bar(s), ph);
-                float4* raw = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + XSTAGE_BYTES);
+            for (int it = 0; it < nit; ++it, ++sc) {
+                if (warp == NPROD + 1) TRACE_AT(sc, 2);
+                mbar_wait(bar.fullx(rx.s), rx.ph);
+                if (warp == NPROD + 1) TRACE_AT(sc, 9);
+                lag.wait(bar);
+                if (warp == NPROD + 1) TRACE_AT(sc, 3);
+                float4* raw = reinterpret_cast<float4*>(smem_gen + rx.s * XSTAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem_gen + Cfg::LO_OFF + rl.s * XSTAGE_BYTES);
                 split_buffer(raw, lo, XSTAGE_BYTES / 16, tid_s, 128);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ready_bar(s));
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (lane == 0) mbar_arrive(bar.ready(rr.s));
+                if (warp == NPROD + 1) TRACE_AT(sc, 4);
+                rx.next(); rl.next(); rr.next();
             }
         }
     } else {
@@ -443,9 +583,10 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int j = 0; j < Cfg::NJ; ++j) creg[j] = 0.f;
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
+#if !defined(PYMFB_EXP_SS_SKIP_DRAIN)
 #pragma unroll
                 for (int j0 = 0; j0 < Cfg::NJ; j0 += 16) {
                     float hi[16], sm[16];
@@ -455,13 +596,16 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
                 }
+#else
+                (void)taddr;
+#endif
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(b));
+                if (lane == 0) mbar_arrive(bar.tempty(b));
             }
             {   // D segment + H update
                 const uint32_t b = g & 1u;
-                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
                 const int col = tile * TILE_COLS + q * 32 + lane;
@@ -491,7 +635,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(b));
+                if (lane == 0) mbar_arrive(bar.tempty(b));
                 ++g;
             }
         }
@@ -502,16 +646,12 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 }
 
 template <int KP>
-struct XCfg {   // X H^T pass
-    static constexpr int HSTAGE_BYTES = 2 * KP * 128;               // [H hi rows | H lo rows] x 32 cols
-    static constexpr int STAGE_BYTES = 2 * XSTAGE_BYTES + HSTAGE_BYTES;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+struct XCfg : SsRings<KP> {   // X H^T pass
+    static constexpr int HSTAGE_BYTES = 2 * KP * 128;               // [H hi rows | H lo rows] x 32 cols (= BSTAGE_BYTES)
     static constexpr int SEG_COLS = 2 * KP;                         // [hi | small]
     static constexpr int EPI_WARPS = KP > 64 ? 8 : 4;
     static constexpr int NJ = KP / (EPI_WARPS / 4);
     static constexpr int THREADS = 32 * (NPROD + 5 + EPI_WARPS);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     static_assert(KP % 32 == 0 && KP >= 32 && KP <= 128, "KP must be 32, 64, 96 or 128");
     static_assert(NJ % 16 == 0, "epilogue column split must be a multiple of 16");
 };
@@ -519,7 +659,8 @@ struct XCfg {   // X H^T pass
 // ---------------------------------------------------------------------------------------------
 // X H^T pass.  Task = (block of 128 rows of X, range of columns).  TMEM lanes = rows of X, TMEM
 // columns = basis index; segments [ X H_hi^T | X H_lo^T + X_lo H_hi^T ] over 256 columns each are
-// summed in registers and flushed once per task with fp32 atomics into P (d x KP).
+// summed in registers and flushed once per task into this split's copy of P (or with fp32 atomics).
+// Same three rings as the H-update pass: warp 0 loads the X boxes, warps 1-2 the [H_hi ; H_lo] chunks.
 // ---------------------------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
@@ -536,31 +677,24 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto ready_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES + 4));
+    const SsBars<Cfg> bar{smem_base + Cfg::BAR_OFF};
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFF + 8 * Cfg::NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapH);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        bar.init(Cfg::EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
+    if (warp == NPROD) tmem_alloc(bar.tmem_slot(), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    auto xraw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto xlo = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };
-    auto hch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + 2 * XSTAGE_BYTES; };
+    auto xraw = [&](int s) { return smem_base + s * XSTAGE_BYTES; };
+    auto xlo = [&](int s) { return smem_base + Cfg::LO_OFF + s * XSTAGE_BYTES; };
+    auto hch = [&](int s) { return smem_base + Cfg::B_OFF + s * Cfg::HSTAGE_BYTES; };
     auto task_chunks = [&](int task, int& c_begin) {     // number of 32-column stages of a task
         // xrev: walk the column ranges from the END of the matrix - the H-update pass that ran just before finished
         // there, so the first tasks find their X columns still in L2 (and this pass ends where the next H-update starts)
@@ -570,38 +704,62 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         return (c_end - c_begin + 31) / 32;
     };
 
-    if (warp < NPROD) {
-        {
-            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % NPROD == warp
-            for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
-                int c_begin;
-                const int nch = task_chunks(task, c_begin);
-                const int row0 = (task % num_rb) * 128;
-                for (int ch = 0; ch < nch; ++ch) {
-                    if (pcnt++ % NPROD == (uint32_t)warp) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+    if (warp == 0) {
+        RingPos<Cfg::NX> rx;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            const int row0 = (task % num_rb) * 128;
+            for (int ch = 0; ch < nch; ++ch) {
+                mbar_wait(bar.done(rx.s), rx.ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar.fullx(rx.s), XSTAGE_BYTES);
+                    tma_load_x(xraw(rx.s), &mapX, bar.fullx(rx.s), c_begin + 32 * ch, row0, xsh);
+                    if (pf > 0 && ch + pf < nch) tma_prefetch_x(&mapX, c_begin + 32 * (ch + pf), row0, xsh);
+                }
+                __syncwarp();
+                rx.next();
+            }
+        }
+    } else if (warp < NPROD) {
+        RingPos<Cfg::NW> rw;
+        DoneLag<Cfg::NX, Cfg::NW> lag;
+        uint32_t cnt = 0;
+        for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
+            int c_begin;
+            const int nch = task_chunks(task, c_begin);
+            for (int ch = 0; ch < nch; ++ch) {
+                const bool mine = cnt++ % (NPROD - 1) == (uint32_t)(warp - 1);
+                lag.wait(bar, mine);
+                if (mine) {
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + 2 * KP * 128);
-                        tma_load_x(xraw(s), &mapX, full_bar(s), c_begin + 32 * ch, row0, xsh);
-                        if (pf > 0 && ch + pf < nch) tma_prefetch_x(&mapX, c_begin + 32 * (ch + pf), row0, xsh);
-                        tma_load_2d(hch(s), &mapH, full_bar(s), 0, ((c_begin >> 5) + ch) * (2 * KP));   // [H_hi ; H_lo] chunk
+#if defined(PYMFB_EXP_SS_SKIP_B)
+                        mbar_arrive(bar.ready(rw.s));
+#else
+                        mbar_expect_tx(bar.ready(rw.s), Cfg::HSTAGE_BYTES);
+                        tma_load_2d(hch(rw.s), &mapH, bar.ready(rw.s), 0, ((c_begin >> 5) + ch) * (2 * KP));   // [H_hi ; H_lo] chunk
+#endif
                     }
                     __syncwarp();
-                    }
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
                 }
+                rw.next();
             }
         }
     } else if (warp == NPROD) {
         {
+#if defined(PYMFB_EXP_SS_HALF_N)
+            constexpr uint32_t idesc_hl = make_idesc(128, KP, 0, 0);
+            constexpr uint32_t idesc_h = make_idesc(128, KP / 2, 0, 0);
+#else
             constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 0);
             constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 0);
-            int s = 0; uint32_t ph = 0; uint32_t g = 0;
-            // K-major SW128 descriptors of stage 0; stage s / k-step ks add (s * STAGE_BYTES + ks * 32) >> 4 to the low words
+#endif
+            RingPos<Cfg::NX> rx; RingPos<Cfg::NL> rl; RingPos<Cfg::NW> rw;
+            uint32_t g = 0;
+            // K-major SW128 descriptors of slot 0 of each ring; slot s / k-step ks add (s * slot bytes + ks * 32) >> 4 to the low words
             const uint64_t xd_hi0 = make_desc(xraw(0), 16, 1024), xd_lo0 = make_desc(xlo(0), 16, 1024), xd_b0 = make_desc(hch(0), 16, 1024);
             const uint32_t xdh = (uint32_t)(xd_hi0 >> 32);
             const uint32_t xahi0 = (uint32_t)xd_hi0, xalo0 = (uint32_t)xd_lo0, xb0 = (uint32_t)xd_b0;
-            uint32_t soff = 0;
             for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
                 int c_begin;
                 const int nch = task_chunks(task, c_begin);
@@ -609,49 +767,67 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 while (ch < nch) {
                     const int seg_end = min(ch + SEG_STAGES, nch);
                     const uint32_t b = g & 1u;
-                    mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar.tempty(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
                     bool first = true;
                     for (; ch < seg_end; ++ch) {
-                        mbar_wait(full_bar(s), ph);
-                        mbar_wait(ready_bar(s), ph);
+                        mbar_wait(bar.ready(rw.s), rw.ph);
                         tc_fence_after();
                         if (elect_one()) {
+                            const uint32_t ox = xahi0 + rx.s * (XSTAGE_BYTES >> 4), ol = xalo0 + rl.s * (XSTAGE_BYTES >> 4);
+                            const uint32_t ob = xb0 + rw.s * (Cfg::HSTAGE_BYTES >> 4);
+#if PYMFB_SS_MMA_ORDER == 0
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint32_t o = soff + ks * (32 >> 4);
-                                umma_tf32_lh(dcol, xahi0 + o, xdh, xb0 + o, xdh, idesc_hl, (first && ks == 0) ? 0u : 1u);
-                                umma_tf32_lh(dcol + KP, xalo0 + o, xdh, xb0 + o, xdh, idesc_h, 1u);
+                                const uint32_t o = ks * (32 >> 4);
+                                umma_tf32_lh(dcol, ox + o, xdh, ob + o, xdh, idesc_hl, (first && ks == 0) ? 0u : 1u);
+                                umma_tf32_lh(dcol + KP, ol + o, xdh, ob + o, xdh, idesc_h, 1u);
                             }
-                            umma_commit(empty_bar(s));
+#elif PYMFB_SS_MMA_ORDER == 1
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32_lh(dcol, ox + ks * (32 >> 4), xdh, ob + ks * (32 >> 4), xdh, idesc_hl, (first && ks == 0) ? 0u : 1u);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32_lh(dcol + KP, ol + ks * (32 >> 4), xdh, ob + ks * (32 >> 4), xdh, idesc_h, 1u);
+#else
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t o = ks * (32 >> 4);
+                                const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                                umma_tf32_lh(dcol, ox + o, xdh, ob + o, xdh, idesc_h, acc);
+                                umma_tf32_lh(dcol + KP, ox + o, xdh, ob + o + (KP * 128 >> 4), xdh, idesc_h, acc);
+                                umma_tf32_lh(dcol + KP, ol + o, xdh, ob + o, xdh, idesc_h, 1u);
+                            }
+#endif
+                            umma_commit(bar.done(rx.s));
+                            if (ch + 1 == seg_end) umma_commit(bar.tfull(b));     // last stage of the segment: hand it to the epilogue
                         }
                         __syncwarp();
                         first = false;
-                        soff += Cfg::STAGE_BYTES >> 4;
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
+                        rx.next(); rl.next(); rw.next();
                     }
-                    if (elect_one()) umma_commit(tfull_bar(b));
-                    __syncwarp();
                     ++g;
                 }
             }
         }
     } else if (warp < NPROD + 5) {
         const int tid_s = threadIdx.x - 32 * (NPROD + 1);
-        int s = 0; uint32_t ph = 0;
+        RingPos<Cfg::NX> rx; RingPos<Cfg::NL> rl; RingPos<Cfg::NR> rr;
+        DoneLag<Cfg::NX, Cfg::NL> lag;
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
             int c_begin;
             const int nch = task_chunks(task, c_begin);
             for (int ch = 0; ch < nch; ++ch) {
-                mbar_wait(full_bar(s), ph);
-                uint8_t* stage = smem_gen + s * Cfg::STAGE_BYTES;
-                split_buffer(reinterpret_cast<float4*>(stage), reinterpret_cast<float4*>(stage + XSTAGE_BYTES),
-                             XSTAGE_BYTES / 16, tid_s, 128);
+                mbar_wait(bar.fullx(rx.s), rx.ph);
+                lag.wait(bar);
+                split_buffer(reinterpret_cast<float4*>(smem_gen + rx.s * XSTAGE_BYTES),
+                             reinterpret_cast<float4*>(smem_gen + Cfg::LO_OFF + rl.s * XSTAGE_BYTES), XSTAGE_BYTES / 16, tid_s, 128);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ready_bar(s));
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (lane == 0) mbar_arrive(bar.ready(rr.s));
+                rx.next(); rl.next(); rr.next();
             }
         }
     } else {
@@ -668,7 +844,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             for (int j = 0; j < Cfg::NJ; ++j) areg[j] = 0.f;
             for (int seg = 0; seg < nseg; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
 #pragma unroll
@@ -682,7 +858,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(b));
+                if (lane == 0) mbar_arrive(bar.tempty(b));
             }
             const int row = (task % num_rb) * 128 + q * 32 + lane;
             if (dbg != nullptr && task == 0) {
@@ -795,19 +971,6 @@ __device__ __forceinline__ void park_hilo(uint32_t taddr, const float (&v)[32]) 
     tmem_st32(taddr, hi);
     tmem_st32(taddr + 32, lo);
 }
-
-// PYMFB_TRACE (experiment builds only): CTA 0 records clock64() at the hand-over points of its first
-// TRACE_STAGES pipeline stages into dbg + 1 MB; dumped by tc_release() to $PYMFB_TRACE_FILE.
-#if defined(PYMFB_TRACE)
-constexpr int TRACE_STAGES = 4096;
-#define TRACE_AT(stage_idx, slot)                                                                           \
-    do {                                                                                                    \
-        if (dbg != nullptr && blockIdx.x == 0 && lane == 0 && (stage_idx) < (uint32_t)TRACE_STAGES)                   \
-            reinterpret_cast<long long*>(dbg + (1 << 18))[(size_t)(stage_idx) * 16 + (slot)] = clock64();   \
-    } while (0)
-#else
-#define TRACE_AT(stage_idx, slot) do { } while (0)
-#endif
 
 template <int KP>
 __global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
