@@ -1287,6 +1287,347 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TS H-update, RS rows per stage (round 2b).  What the commit / MMA-group probe (tests/commit_probe.cu) and the
+// PYMFB_TRACE timeline say about the 32-row kernel above at k = 64: its 8 MMAs per stage are short (64 + 32 tensor
+// cycles per k-step), tcgen05.mma issue blocks on a shallow queue, so the ~300 cycles the MMA warp spends per stage on
+// its barrier wait, two commits and loop bookkeeping are NOT hidden behind tensor work: 560-650 cycles per stage
+// against 385 of tensor time.  This variant halves that overhead per byte: a stage is RS = 64 rows (16 MMAs per wait),
+// and ONE tcgen05.commit per stage (done[s]) frees the X / operand slot and - NT stages later - the TMEM A slot that
+// the convert warps wait for (DoneLag), instead of separate empty / aempty commits.
+// ---------------------------------------------------------------------------------------------
+template <int KP, int RS>
+struct TsrCfg {
+    static constexpr int NCH = 2 * KP / 32;
+    static constexpr int XS_BYTES = TILE_COLS * RS * 4;             // plain [RS rows][128 cols]
+    static constexpr int BSTAGE_BYTES = NCH * RS * 128;             // [b_hi | b_lo] chunks, RS rows each
+    static constexpr int STAGE_BYTES = XS_BYTES + BSTAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int NCHAIN = (KP == 32) ? PYMFB_NCHAIN : 1;
+    static constexpr int CHAIN_COLS = 2 * KP;
+    static constexpr int SEG_COLS = CHAIN_COLS * NCHAIN;
+    static constexpr int A_COL0 = 2 * SEG_COLS;
+    static constexpr int ASLOT_COLS = 2 * RS;                       // RS hi columns then RS lo columns
+    static constexpr int NT_RAW = (512 - A_COL0) / ASLOT_COLS;
+    static constexpr int NT = NT_RAW > STAGES ? STAGES : (NT_RAW > 6 ? 6 : NT_RAW);
+    static constexpr int EPI_WARPS = 4;
+    static constexpr int THREADS = 32 * (NPROD + 1 + 4 + EPI_WARPS);
+    static constexpr int NBAR = 2 * STAGES + NT + 4;                // full, done, afull, tfull[2], tempty[2]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+    static_assert(KP == 32 || KP == 64, "TS kernels serve KP = 32 and 64");
+    static_assert(RS == 32 || RS == 64, "32 or 64 rows per stage");
+    static_assert(NT >= 2 && NT <= STAGES, "A ring depth");
+    static_assert(STAGES >= 2, "stage ring depth");
+    static_assert(NBAR * 8 + 8 <= 512, "barrier area too small");
+    static_assert(SMEM_BYTES <= SMEM_LIMIT, "stage ring does not fit");
+};
+
+// hi/lo of 32 values -> TMEM (this thread's lane): hi at columns hi_addr.., lo at lo_addr..
+__device__ __forceinline__ void park_hilo_at(uint32_t hi_addr, uint32_t lo_addr, const float (&v)[32]) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+    }
+    tmem_st32(hi_addr, hi);
+    tmem_st32(lo_addr, lo);
+}
+
+template <int KP, int RS>
+__global__ void __launch_bounds__(TsrCfg<KP, RS>::THREADS, 1)
+k_h_update_tsr(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+               const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
+               const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
+               float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
+               int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
+               const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum, int xsh) {
+    // same contract as k_h_update_ts; seg_c counts stages of RS rows; the boxes of mapX / mapH are 128 columns x RS
+    // rows, those of mapW / mapG 32 columns x RS rows (rows beyond the matrix read as zero)
+#if !defined(PYMFB_TS_NO_CENTER)
+    __shared__ float s_mean[2 * KP];          // [w_mean | g_mean]: read on the critical tail of every tile, so not from global
+    if (threadIdx.x < 2 * KP)
+        s_mean[threadIdx.x] = (wmean == nullptr) ? 0.f : (threadIdx.x < KP ? wmean[threadIdx.x] : gmean[threadIdx.x - KP]);
+#endif
+    const int segc = seg_c;
+    using Cfg = TsrCfg<KP, RS>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    struct Bars {
+        uint32_t base;
+        __device__ __forceinline__ uint32_t full(int s) const { return base + 8u * s; }
+        __device__ __forceinline__ uint32_t done(int s) const { return base + 8u * (Cfg::STAGES + s); }
+        __device__ __forceinline__ uint32_t afull(int t) const { return base + 8u * (2 * Cfg::STAGES + t); }
+        __device__ __forceinline__ uint32_t tfull(int a) const { return base + 8u * (2 * Cfg::STAGES + Cfg::NT + a); }
+        __device__ __forceinline__ uint32_t tempty(int a) const { return base + 8u * (2 * Cfg::STAGES + Cfg::NT + 2 + a); }
+    };
+    const Bars bar{bar_base};
+    auto bar_tfull = [&](int a) { return bar.tfull(a); };
+    auto bar_tempty = [&](int a) { return bar.tempty(a); };
+    const uint32_t tmem_slot = bar_base + 8u * Cfg::NBAR;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar.full(s), 1); mbar_init(bar.done(s), 1); }
+        for (int t = 0; t < Cfg::NT; ++t) mbar_init(bar.afull(t), 4);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar.tfull(a), 1); mbar_init(bar.tempty(a), Cfg::EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int nd = (d + RS - 1) / RS;
+    const int nit = nd + (KP + RS - 1) / RS;
+    auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                    // [RS rows][128 cols] plain
+    auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::XS_BYTES; };       // MN-major chunks
+
+    if (warp < NPROD) {
+        RingPos<Cfg::STAGES> rs;
+        uint32_t pcnt = 0;                               // this warp issues stages pcnt % NPROD == warp
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int col0 = tile * TILE_COLS;
+            for (int it = 0; it < nit; ++it) {
+                if (pcnt++ % NPROD == (uint32_t)warp) {
+                    TRACE_AT(pcnt - 1, 0);
+                    mbar_wait(bar.done(rs.s), rs.ph ^ 1);
+                    TRACE_AT(pcnt - 1, 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar.full(rs.s), Cfg::XS_BYTES + Cfg::BSTAGE_BYTES);
+                        const bool xphase = it < nd;
+                        const int r0 = (xphase ? it : it - nd) * RS;
+                        tma_load_x(xs_addr(rs.s), xphase ? &mapX : &mapH, bar.full(rs.s), col0, r0, xphase ? xsh : kNoPanel);
+                        const CUtensorMap* mb = xphase ? &mapW : &mapG;
+#pragma unroll
+                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(rs.s) + c * (RS * 128), mb, bar.full(rs.s), 32 * c, r0);
+                    }
+                    __syncwarp();
+                }
+                rs.next();
+            }
+        }
+    } else if (warp == NPROD) {
+        constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
+        constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
+        RingPos<Cfg::STAGES> rs; RingPos<Cfg::NT> rt;
+        uint32_t g = 0, mc = 0; (void)mc;
+        // [W_hi|W_lo] / [G_hi|G_lo] operand descriptor of stage 0; stage s, k-group kg add (s * STAGE_BYTES + kg * 1024) >> 4
+        // to the low word (shared-memory addresses are < 2^18, so the 14-bit address field never carries)
+        const uint64_t bd0 = make_desc(wch(0), RS * 128, 512, 1);
+        const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo0 = (uint32_t)bd0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int it = 0;
+            while (it < nit) {
+                const int seg_end = (it < nd) ? min(it + segc, nd) : nit;
+                const uint32_t b = g & 1u;
+                mbar_wait(bar.tempty(b), ((g >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                bool first = true;
+                for (; it < seg_end; ++it, ++mc) {
+                    TRACE_AT(mc, 5);
+                    // afull(t) implies full(s): the convert warps waited on full(s) - the barrier that also counts the
+                    // [W_hi|W_lo] bytes of the stage - before they filled A slot t and arrived on afull(t)
+                    mbar_wait(bar.afull(rt.s), rt.ph);
+                    TRACE_AT(mc, 6);
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + Cfg::A_COL0 + rt.s * Cfg::ASLOT_COLS;
+                    if (elect_one()) {
+                        const uint32_t bl = bd_lo0 + rs.s * (Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+                        for (int kg = 0; kg < RS / 8; ++kg) {
+                            const uint32_t dc = dcol + (kg % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
+                            umma_tf32_ts_lh(dc, a_hi + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
+                            umma_tf32_ts_lh(dc + KP, a_hi + RS + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_h, 1u);
+                        }
+                        TRACE_AT(mc, 14);
+                        umma_commit(bar.done(rs.s));                          // frees the stage and (NT stages on) its A slot
+                        if (it + 1 == seg_end) umma_commit(bar.tfull(b));
+                    }
+                    __syncwarp();
+                    TRACE_AT(mc, 7);
+                    first = false;
+                    rs.next(); rt.next();
+                }
+                ++g;
+            }
+        }
+    } else if (warp < NPROD + 5) {
+        // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
+        const int q = warp & 3;
+        const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
+        RingPos<Cfg::STAGES> rs; RingPos<Cfg::NT> rt;
+        DoneLag<Cfg::STAGES, Cfg::NT> lag;
+        uint32_t cc = 0; (void)cc;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; it < nit; ++it, ++cc) {
+                if (q == 0) TRACE_AT(cc, 2);
+                mbar_wait(bar.full(rs.s), rs.ph);
+                if (q == 0) TRACE_AT(cc, 9);
+                lag.wait(bar);                            // the MMAs that read this A slot NT stages ago have completed
+                if (q == 0) TRACE_AT(cc, 3);
+                tc_fence_after();
+                const float* xs = reinterpret_cast<const float*>(smem_gen + rs.s * Cfg::STAGE_BYTES);
+                const uint32_t slot = lane_addr + rt.s * Cfg::ASLOT_COLS;
+#pragma unroll
+                for (int h = 0; h < RS / 32; ++h) {
+                    float v[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = xs[(h * 32 + r) * TILE_COLS + mylane];
+                    park_hilo_at(slot + h * 32, slot + RS + h * 32, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (q == 0) TRACE_AT(cc, 4);
+                if (lane == 0) mbar_arrive(bar.afull(rt.s));
+                rs.next(); rt.next();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int nsegC = (nd + segc - 1) / segc;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            float creg[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) creg[j] = 0.f;
+            // Old H of this lane's column, fetched NOW: under a saturated memory system a dependent
+            // global load takes ~3 us, and doing it after the last segment stalled every tile by ~10 us.
+            const int col = tile * TILE_COLS + q * 32 + lane;
+            // KP = 64 sits at the register cap of this kernel (168): holding the old H column (64 values) next to
+            // the 64 sums through the whole tile made the compiler spill and cost the pass 20 % once the centering
+            // terms were added (same-box bisect).  LEAN: the column is pulled into L2 when the last W^T X segment
+            // starts, summed (and thereby pulled into L1) while the G H MMAs are in flight, and re-read 16 values at a time.
+            constexpr bool LEAN = (KP == 64);
+            float hreg[LEAN ? 1 : KP];
+            float xs = 0.f;
+            if constexpr (!LEAN) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
+                xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+            }
+            for (int seg = 0; seg < nsegC; ++seg, ++g) {
+                if constexpr (LEAN) {
+                    if (seg == nsegC - 1 && col < n_loc) {
+#pragma unroll 8
+                        for (int j = 0; j < KP; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(Hc + (int64_t)j * ldh + col));
+                        if (wmean != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(xsum + col));
+                    }
+                }
+                const uint32_t b = g & 1u;
+                if (q == 0) TRACE_AT(g * segc, 10);
+                mbar_wait(bar_tfull(b), (g >> 1) & 1u);
+                if (q == 0) TRACE_AT(g * segc, 11);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+#pragma unroll
+                    for (int ch = 0; ch < Cfg::NCHAIN; ++ch) {
+                        float hi[16], sm[16];
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + j0, hi);
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + KP + j0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (q == 0) TRACE_AT(g * segc, 12);
+                if (lane == 0) mbar_arrive(bar_tempty(b));
+            }
+            {
+                float hsum = 0.f;                     // column sum of the old H tile (for the centered G H)
+                if constexpr (LEAN) {
+                    if (col < n_loc) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += __ldg(Hc + (int64_t)j * ldh + col);
+                        if (wmean != nullptr) xs = __ldg(xsum + col);
+                    }
+                } else {
+                    if (wmean != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += hreg[j];
+                    }
+                }
+                const uint32_t b = g & 1u;
+                mbar_wait(bar_tfull(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+                    float dh[16], dl[16];
+                    tmem_ld16(taddr + j0, dh);
+                    tmem_ld16(taddr + KP + j0, dl);
+                    tmem_ld_wait();
+                    if (Cfg::NCHAIN > 1) {
+                        float eh[16], el[16];
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + j0, eh);
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + KP + j0, el);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { dh[j] += eh[j]; dl[j] += el[j]; }
+                    }
+                    if (dbg != nullptr && tile == 0) {
+                        float* o = dbg + (size_t)(q * 32 + lane) * (2 * KP) + j0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { o[j] = creg[j0 + j]; o[KP + j] = dh[j] + dl[j]; }
+                    }
+#if defined(PYMFB_EXP_SKIP_EPI_GLOBAL)
+                    if (col < -1) {
+#else
+                    if (col < n_loc) {
+#endif
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int64_t o = (int64_t)(j0 + j) * ldh + col;
+                            float h;
+                            if constexpr (LEAN) h = __ldg(Hc + o); else h = hreg[j0 + j];
+                            float cj = creg[j0 + j], dj = dh[j] + dl[j];
+#if !defined(PYMFB_TS_NO_CENTER)
+                            if (wmean != nullptr) {
+#if defined(PYMFB_MEAN_LDG)
+                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
+                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+#else
+                                cj = fmaf(s_mean[j0 + j], xs, cj);
+                                dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
+#endif
+                            }
+#endif
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
+                            const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
+                            Hn[o] = hn;                                  // new H
+                            Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[hs_index(KP + (j0 + j), col, 2 * KP)] = hn - hh;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty(b));
+                ++g;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
+}
+
+
 constexpr int X_CONV_GROUPS = 2;                          // convert-warp groups of the X.H^T pass (alternate stages)
 constexpr int X_THREADS = 32 * (NPROD + 1 + 4 * X_CONV_GROUPS + 4);
 
@@ -1648,6 +1989,8 @@ struct TcPlan {
     CUtensorMap mapW_b[4], mapG_b[4], mapH_xb[2][4];   // per-block maps (k > 128)
     CUtensorMap mapX_h, mapX_x, mapW, mapG, mapH_h[2], mapH_x[2];
     CUtensorMap mapX_p, mapH_p[2];   // TS kernels: plain (unswizzled) 128-column x 32-row boxes
+    CUtensorMap mapX_p64, mapH_p64[2], mapW64, mapG64;   // the same with 64-row boxes (k_h_update_tsr<KP, 64>)
+    int ts_rs = 64;                  // rows per stage of the TS H-update kernel (PYMFB_TS_RS=32: the round-1 kernel)
     CUtensorMap mapH_a[2];           // H as the A operand of the H.H^T tasks (128-row boxes, rows >= kp zero-filled)
     int hh_tasks = 0, hh_cols_per_task = 0;
     bool use_ts = false;             // k <= 64: A operand from TMEM (k_*_ts), else both operands in smem
@@ -1755,6 +2098,10 @@ inline int ts_set_attrs() {
     cudaError_t e = cudaFuncSetAttribute(tc::k_h_update_ts<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsCfg<KP>::SMEM_BYTES);
     if (e != cudaSuccess) return 1;
     e = cudaFuncSetAttribute(tc::k_xht_ts<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsCfg<KP>::SMEM_BYTES);
+    if (e != cudaSuccess) return 1;
+    e = cudaFuncSetAttribute(tc::k_h_update_tsr<KP, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsrCfg<KP, 64>::SMEM_BYTES);
+    if (e != cudaSuccess) return 1;
+    e = cudaFuncSetAttribute(tc::k_h_update_tsr<KP, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsrCfg<KP, 32>::SMEM_BYTES);
     return e == cudaSuccess ? 0 : 1;
 }
 
@@ -1840,7 +2187,18 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     // instruction instead of the 3-D one, was measured: no difference)
     ok = ok && make_map3(&p.mapX_p, X, d, n_loc, ldx, xps, xsh64, tc::TILE_COLS, tc::R1, 0, &p.err);
     for (int i = 0; i < 2; ++i) ok = ok && make_map3(&p.mapH_p[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, tc::TILE_COLS, tc::R1, 0, &p.err);
+    if (kp <= 64) {      // 64-row boxes of the TS H-update kernel (rows beyond the matrix - H and G have kp rows - read as zero)
+        ok = ok && make_map3(&p.mapX_p64, X, d, n_loc, ldx, xps, xsh64, tc::TILE_COLS, 64, 0, &p.err);
+        for (int i = 0; i < 2; ++i) ok = ok && make_map3(&p.mapH_p64[i], p.Hbuf[i], kp, n_loc, ldh, 0, kNoPanelShift, tc::TILE_COLS, 64, 0, &p.err);
+        ok = ok && make_map(&p.mapW64, p.Wsplit, d, 2 * p.kpb, 2 * p.kpb, 64, true, &p.err);
+        ok = ok && make_map(&p.mapG64, p.Gsplit, kp, 2 * p.kpb, 2 * p.kpb, 64, true, &p.err);
+    }
     if (!ok) return 1;
+    // TS H-update kernel: k <= 32 runs k_h_update_tsr with 64-row stages (cfg2 0.674 -> 0.664 ms, 8192 x 524288 k=32 2.97 -> 2.69 ms);
+    // k = 64 keeps k_h_update_ts (32 rows, separate empty / aempty commits): there 64-row stages leave only two TMEM A slots
+    // (4.07-4.28 vs 3.71 ms on cfg4 k=64) and the single-commit 32-row variant measured 3.86-3.94 vs 3.71 ms, same box.
+    // PYMFB_TS_RS = 64 / 32 force k_h_update_tsr<KP, 64 / 32>, 1 forces k_h_update_ts.
+    { const char* e = getenv("PYMFB_TS_RS"); p.ts_rs = e ? atoi(e) : (kp == 32 ? 64 : 1); }
     {
         const char* force_ss = getenv("PYMFB_TC_FORCE_SS");
         p.use_ts = kp <= 64 && !(force_ss && force_ss[0] == '1');
@@ -1967,6 +2325,18 @@ inline int grid_cap(int grid) {
 template <int KP>
 inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cudaStream_t stream) {
     const int grid = grid_cap(std::min(p.h_tiles, p.sm_count));
+    if (p.ts_rs == 64) {
+        tc::k_h_update_tsr<KP, 64><<<grid, tc::TsrCfg<KP, 64>::THREADS, tc::TsrCfg<KP, 64>::SMEM_BYTES, stream>>>(
+            p.mapX_p64, p.mapW64, p.mapH_p64[hsrc], p.mapG64, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
+            std::max(1, p.seg_c / 2), p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
+        return;
+    }
+    if (p.ts_rs == 32) {
+        tc::k_h_update_tsr<KP, 32><<<grid, tc::TsrCfg<KP, 32>::THREADS, tc::TsrCfg<KP, 32>::SMEM_BYTES, stream>>>(
+            p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
+            p.seg_c, p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
+        return;
+    }
     tc::k_h_update_ts<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
         p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.seg_c, p.lam_h, p.Dp, p.Dn,
         p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);

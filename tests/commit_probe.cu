@@ -10,7 +10,7 @@
 using namespace pymfb;
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
-__global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups, int waits, long long* out) {
+__global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups, int waits, long long* out, int ts, int nbig) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups
     tc::tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + 16384 + 32768 + 64);
     if (warp == 0) {
-        const uint32_t id256 = tc::make_idesc(128, 256, 0, 0), id128 = tc::make_idesc(128, 128, 0, 0);
+        const uint32_t id256 = tc::make_idesc(128, nbig, 0, 0), id128 = tc::make_idesc(128, nbig / 2, 0, 0);
         long long t0 = 0, t1 = 0;
         for (int rep = 0; rep < 2; ++rep) {
             t0 = clock64();
@@ -38,8 +38,13 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups
 #pragma unroll 8
                     for (int i = 0; i < n; ++i) {
                         const uint64_t ad = tc::make_desc(a_addr + (i & 3) * 32, 16, 1024), bd = tc::make_desc(b_addr + (i & 3) * 32, 16, 1024);
-                        if (i & 1) tc::umma_tf32(tmem + 128, ad, bd, id128, 1u);
-                        else tc::umma_tf32(tmem, ad, bd, id256, 1u);
+                        if (ts) {
+                            if (i & 1) tc::umma_tf32_ts(tmem + nbig / 2, tmem + 448 + (i & 3) * 8, bd, id128, 1u);
+                            else tc::umma_tf32_ts(tmem, tmem + 416 + (i & 3) * 8, bd, id256, 1u);
+                        } else {
+                            if (i & 1) tc::umma_tf32(tmem + nbig / 2, ad, bd, id128, 1u);
+                            else tc::umma_tf32(tmem, ad, bd, id256, 1u);
+                        }
                     }
                     for (int c = 0; c < ncommit; ++c) tc::umma_commit(bar + 8 * (1 + c));
                 }
@@ -63,16 +68,18 @@ int main() {
     const int smem = 16384 + 32768 + 2048;
     CHECK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int groups = 2048;
-    for (int grid : {1, 148})
-        for (int waits : {0, 1})
-            for (int n : {2, 4, 8, 16})
-                for (int nc : {0, 1, 2, 3}) {
-                    k_probe<<<grid, 128, smem>>>(n, nc, groups, waits, dout);
-                    CHECK(cudaDeviceSynchronize());
-                    long long cyc = 0;
-                    CHECK(cudaMemcpy(&cyc, dout, sizeof(cyc), cudaMemcpyDeviceToHost));
-                    printf("grid %3d waits %d  MMAs/group %2d  commits/group %d : %7.1f cycles/group  (tensor time %d)\n", grid, waits, n, nc,
-                           (double)cyc / groups, n / 2 * 192);
-                }
+    for (int ts : {0, 1})
+        for (int nbig : {256, 128, 64})
+            for (int waits : {0, 1})
+                for (int n : {4, 8, 16, 32})
+                    for (int nc : {0, 1, 2}) {
+                        if (ts == 0 && nbig != 256) continue;
+                        k_probe<<<148, 128, smem>>>(n, nc, groups, waits, dout, ts, nbig);
+                        CHECK(cudaDeviceSynchronize());
+                        long long cyc = 0;
+                        CHECK(cudaMemcpy(&cyc, dout, sizeof(cyc), cudaMemcpyDeviceToHost));
+                        printf("%s N %3d/%3d waits %d  MMAs/group %2d  commits/group %d : %7.1f cycles/group  (tensor time %d)\n", ts ? "TS" : "SS", nbig, nbig / 2,
+                               waits, n, nc, (double)cyc / groups, n / 2 * (nbig / 2 + nbig / 4));
+                    }
     return 0;
 }
