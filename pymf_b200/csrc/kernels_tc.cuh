@@ -88,6 +88,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (((++spins) & 0xFFu) == 0u) mbar_watchdog(t0);
     }
 }
+// Wait of a warp that has slack (epilogue warps between segments, TMA producers behind a full ring): back off between
+// polls instead of re-issuing try_wait back to back - fewer issue slots and less power for the warps on the critical path.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#if defined(PYMFB_RELAXED_WAIT)
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(PYMFB_RELAXED_WAIT);
+        if (((++spins) & 0xFFu) == 0u) mbar_watchdog(t0);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // One elected lane of a CONVERGED warp.  The producer and MMA warps run their loops with all 32 lanes
 // (warp-uniform control flow lets the compiler keep descriptors / addresses in uniform registers; a
 // lane-0-only branch made every tcgen05.mma cost ~90 issue cycles) and elect one lane per issue.
@@ -427,7 +442,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             const int col0 = tile * TILE_COLS;
             for (int it = 0; it < nit; ++it, ++tc_) {
                 TRACE_AT(tc_, 0);
-                mbar_wait(bar.done(rx.s), rx.ph ^ 1);
+                mbar_wait_relaxed(bar.done(rx.s), rx.ph ^ 1);
                 TRACE_AT(tc_, 1);
                 if (elect_one()) {
                     mbar_expect_tx(bar.fullx(rx.s), XSTAGE_BYTES);
@@ -583,7 +598,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             for (int j = 0; j < Cfg::NJ; ++j) creg[j] = 0.f;
             for (int seg = 0; seg < nsegC; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
+                mbar_wait_relaxed(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
 #if !defined(PYMFB_EXP_SS_SKIP_DRAIN)
@@ -605,7 +620,7 @@ k_h_update_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
             }
             {   // D segment + H update
                 const uint32_t b = g & 1u;
-                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
+                mbar_wait_relaxed(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
                 const int col = tile * TILE_COLS + q * 32 + lane;
@@ -711,7 +726,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             const int nch = task_chunks(task, c_begin);
             const int row0 = (task % num_rb) * 128;
             for (int ch = 0; ch < nch; ++ch) {
-                mbar_wait(bar.done(rx.s), rx.ph ^ 1);
+                mbar_wait_relaxed(bar.done(rx.s), rx.ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(bar.fullx(rx.s), XSTAGE_BYTES);
                     tma_load_x(xraw(rx.s), &mapX, bar.fullx(rx.s), c_begin + 32 * ch, row0, xsh);
@@ -844,7 +859,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             for (int j = 0; j < Cfg::NJ; ++j) areg[j] = 0.f;
             for (int seg = 0; seg < nseg; ++seg, ++g) {
                 const uint32_t b = g & 1u;
-                mbar_wait(bar.tfull(b), (g >> 1) & 1u);
+                mbar_wait_relaxed(bar.tfull(b), (g >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS + jbase;
 #pragma unroll
@@ -1296,6 +1311,9 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
 // and ONE tcgen05.commit per stage (done[s]) frees the X / operand slot and - NT stages later - the TMEM A slot that
 // the convert warps wait for (DoneLag), instead of separate empty / aempty commits.
 // ---------------------------------------------------------------------------------------------
+#ifndef PYMFB_TSR_CONV_GROUPS
+#define PYMFB_TSR_CONV_GROUPS 2
+#endif
 template <int KP, int RS>
 struct TsrCfg {
     static constexpr int NCH = 2 * KP / 32;
@@ -1312,7 +1330,12 @@ struct TsrCfg {
     static constexpr int NT_RAW = (512 - A_COL0) / ASLOT_COLS;
     static constexpr int NT = NT_RAW > STAGES ? STAGES : (NT_RAW > 6 ? 6 : NT_RAW);
     static constexpr int EPI_WARPS = 4;
-    static constexpr int THREADS = 32 * (NPROD + 1 + 4 + EPI_WARPS);
+    // Convert-warp groups (4 warps each) taking alternate stages.  PYMFB_TRACE of the one-group kernel with 64-row stages at
+    // k = 32: the group needs 545 cycles per stage + ~300 of waits, the MMA warp 470 + ~180 - the converts bound the
+    // per-SM rate.  A group only sees every CG-th phase of the barriers it waits on, so the ring depth must be a multiple
+    // of CG (a parity wait that skips a phase can alias).
+    static constexpr int CG = (RS == 64 && STAGES % 2 == 0) ? PYMFB_TSR_CONV_GROUPS : 1;
+    static constexpr int THREADS = 32 * (NPROD + 1 + 4 * CG + EPI_WARPS);
     static constexpr int NBAR = 2 * STAGES + NT + 4;                // full, done, afull, tfull[2], tempty[2]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
     static_assert(KP == 32 || KP == 64, "TS kernels serve KP = 32 and 64");
@@ -1460,16 +1483,19 @@ k_h_update_tsr(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 ++g;
             }
         }
-    } else if (warp < NPROD + 5) {
-        // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
+    } else if (warp < NPROD + 1 + 4 * Cfg::CG) {
+        // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring (CG groups take alternate stages) =====
         const int q = warp & 3;
+        const int group = (warp - (NPROD + 1)) >> 2;
         const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
         RingPos<Cfg::STAGES> rs; RingPos<Cfg::NT> rt;
         DoneLag<Cfg::STAGES, Cfg::NT> lag;
-        uint32_t cc = 0; (void)cc;
+        uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int it = 0; it < nit; ++it, ++cc) {
+                const bool mine = Cfg::CG == 1 || (int)(cc % Cfg::CG) == group;
+                if (!mine) { lag.wait(bar, false); rs.next(); rt.next(); continue; }
                 if (q == 0) TRACE_AT(cc, 2);
                 mbar_wait(bar.full(rs.s), rs.ph);
                 if (q == 0) TRACE_AT(cc, 9);
