@@ -1302,6 +1302,332 @@ k_h_update_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ 
     if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
+// k_h_update_ts with two producer warps and TWO MMA-issuing warps (see the comment in the MMA branch).
+template <int KP>
+__global__ void __launch_bounds__(TsCfg<KP>::THREADS, 1)
+k_h_update_ts2w(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+              const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapG,
+              const DevState* __restrict__ st, const float* __restrict__ Hc, float* __restrict__ Hn,
+              float* __restrict__ Hs, int64_t ldh, int d, int n_loc, int num_tiles, float* __restrict__ dbg,
+              int seg_c, float lam, const float* __restrict__ Dp, const float* __restrict__ Dn,
+              const float* __restrict__ wmean, const float* __restrict__ gmean, const float* __restrict__ xsum, int xsh) {
+    // wmean != nullptr: the B operands are the CENTERED W / G (k_split_hilo_centered); the epilogue adds
+    // wmean[j] * (column sum of X) to W^T X and gmean[j] * (column sum of the H tile) to G H
+    // Dp != nullptr: Semi-NMF (pymf/snmf.py:72-90) - the epilogue takes G+ H and G- H from Dp / Dn (same layout
+    // as H, written by k_gh_posneg_simt) instead of the G H accumulator
+#if !defined(PYMFB_TS_NO_CENTER)
+    __shared__ float s_mean[2 * KP];          // [w_mean | g_mean]: read on the critical tail of every tile, so not from global
+    if (threadIdx.x < 2 * KP)
+        s_mean[threadIdx.x] = (wmean == nullptr) ? 0.f : (threadIdx.x < KP ? wmean[threadIdx.x] : gmean[threadIdx.x - KP]);
+#endif
+#if defined(PYMFB_TS_SEG_CONST)
+    constexpr int segc = SEG_STAGES;          // A/B builds: compile-time segment length as in round 1
+#else
+    const int segc = seg_c;
+#endif
+    using Cfg = TsCfg<KP>;
+    if (st->stop) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto afull_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + t); };
+    auto aempty_bar = [&](int t) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NT + t); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NT + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * Cfg::NBAR;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * Cfg::NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapH); tma_prefetch_desc(&mapG);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int t = 0; t < Cfg::NT; ++t) { mbar_init(afull_bar(t), 4); mbar_init(aempty_bar(t), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == NPROD) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int nd = (d + R1 - 1) / R1;
+    const int nit = nd + KP / R1;
+    auto xs_addr = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };                    // [32 rows][128 cols] plain
+    auto wch = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + XSTAGE_BYTES; };        // MN-major chunks
+
+    if (warp < 2) {
+        {
+            int s = 0; uint32_t ph = 0; uint32_t pcnt = 0;   // this warp issues stages pcnt % 2 == warp
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int col0 = tile * TILE_COLS;
+                for (int it = 0; it < nit; ++it) {
+                    if (pcnt++ % 2 == (uint32_t)warp) {
+                    TRACE_AT(pcnt - 1, 0);
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    TRACE_AT(pcnt - 1, 1);
+                    if (elect_one()) {
+#if defined(PYMFB_EXP_SKIP_WLOAD)
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES);
+#else
+                        mbar_expect_tx(full_bar(s), XSTAGE_BYTES + Cfg::BSTAGE_BYTES);
+#endif
+                        const bool xphase = it < nd;
+                        const int r0 = (xphase ? it : it - nd) * R1;
+                        tma_load_x(xs_addr(s), xphase ? &mapX : &mapH, full_bar(s), col0, r0, xphase ? xsh : kNoPanel);
+#if !defined(PYMFB_EXP_SKIP_WLOAD)
+                        const CUtensorMap* mb = xphase ? &mapW : &mapG;
+#pragma unroll
+                        for (int c = 0; c < Cfg::NCH; ++c) tma_load_2d(wch(s) + c * (R1 * 128), mb, full_bar(s), 32 * c, r0);
+#endif
+                    }
+                    __syncwarp();
+                    }
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // ===== two MMA issuers, alternate stages.  tcgen05.mma issue blocks on the tensor pipe's short queue, so what ONE
+        // issuing warp spends per stage on its barrier wait, commits and bookkeeping (~270 cycles) is a pipe bubble when
+        // the MMAs are short (k = 64: 385 tensor cycles per stage, 560-650 measured).  Here warp `mw` owns the stages with
+        // mc % 2 == mw and does that work while the other warp's MMAs are being issued; a named-barrier hand-over
+        // (tcgen05.fence::before_thread_sync / bar.arrive -> bar.sync / tcgen05.fence::after_thread_sync) keeps the MMAs of
+        // consecutive stages in order, so results stay bit-identical to the one-warp kernel.  Each commit tracks the issuing
+        // thread's own MMAs; the pipe completes MMAs in issue order, so a stage's commit also covers the earlier stages.
+        {
+            static_assert(Cfg::NT % 2 == 0, "each A slot must always belong to the same MMA warp (consecutive barrier phases)");
+            const uint32_t mw = (uint32_t)(warp - 2);
+            constexpr uint32_t idesc_hl = make_idesc(128, 2 * KP, 0, 1);
+            constexpr uint32_t idesc_h = make_idesc(128, KP, 0, 1);
+            int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t g = 0; uint32_t mc = 0;
+            const uint64_t bd0 = make_desc(wch(0), R1 * 128, 512, 1);
+            const uint32_t bd_hi = (uint32_t)(bd0 >> 32), bd_lo0 = (uint32_t)bd0;
+            uint32_t soff = 0;
+            const uint32_t my_tiles = (uint32_t)((num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total = my_tiles * (uint32_t)nit;      // stages of this CTA (the last one hands over to nobody)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int it = 0;
+                while (it < nit) {
+                    const int seg_end = (it < nd) ? min(it + segc, nd) : nit;
+                    const uint32_t b = g & 1u;
+                    const uint32_t dcol = tmem_base + b * Cfg::SEG_COLS;
+                    bool first = true;
+                    for (; it < seg_end; ++it, ++mc) {
+                        if ((mc & 1u) == mw) {
+                            TRACE_AT(mc, 5);
+                            if (first) mbar_wait(tempty_bar(b), ((g >> 1) & 1u) ^ 1u);     // the segment's accumulator has been drained
+                            // afull(t) implies full(s) (see k_h_update_ts)
+                            mbar_wait(afull_bar(t), tph);
+                            TRACE_AT(mc, 6);
+                            if (mc > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)mw) : "memory");   // stage mc - 1 has been issued
+                            tc_fence_after();
+                            const uint32_t a_hi = tmem_base + Cfg::A_COL0 + t * 64;
+                            if (elect_one()) {
+                                const uint32_t bl = bd_lo0 + soff;
+#pragma unroll
+                                for (int kg = 0; kg < R1 / 8; ++kg) {
+                                    const uint32_t dc = dcol + (kg % Cfg::NCHAIN) * Cfg::CHAIN_COLS;
+                                    umma_tf32_ts_lh(dc, a_hi + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_hl, (first && kg < Cfg::NCHAIN) ? 0u : 1u);
+                                    umma_tf32_ts_lh(dc + KP, a_hi + 32 + kg * 8, bl + kg * (1024 >> 4), bd_hi, idesc_h, 1u);
+                                }
+                            }
+                            __syncwarp();
+                            tc_fence_before();
+                            if (mc + 1 < total) asm volatile("bar.arrive %0, 64;" ::"r"(1 + (int)(mw ^ 1u)) : "memory");
+                            if (elect_one()) {
+                                umma_commit(empty_bar(s));
+                                umma_commit(aempty_bar(t));
+                                if (it + 1 == seg_end) umma_commit(tfull_bar(b));
+                            }
+                            __syncwarp();
+                            TRACE_AT(mc, 7);
+                        }
+                        first = false;
+                        soff += Cfg::STAGE_BYTES >> 4;
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; soff = 0; }
+                        if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                    }
+                    ++g;
+                }
+            }
+            (void)ph;
+        }
+    } else if (warp < NPROD + 1 + 4 * Cfg::CONV_GROUPS) {
+        // ===== convert warps: smem X tile -> registers -> hi/lo -> TMEM A ring =====
+        // CONV_GROUPS groups of 4 warps take alternate stages (every waiter still sees consecutive phases of the
+        // barriers it waits on: a slot's next use needs this group's own arrival first)
+        const int q = warp & 3;
+        const int group = (warp - (NPROD + 1)) >> 2;
+        const int mylane = q * 32 + lane;                 // column of the tile = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0;
+        int s = 0; uint32_t ph = 0; int t = 0; uint32_t tph = 0; uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; it < nit; ++it, ++cc) {
+                if (Cfg::CONV_GROUPS > 1 && (int)(cc % Cfg::CONV_GROUPS) != group) {
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                    if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+                    continue;
+                }
+                if (q == 0) TRACE_AT(cc, 2);
+                mbar_wait(full_bar(s), ph);
+                if (q == 0) TRACE_AT(cc, 9);
+                mbar_wait(aempty_bar(t), tph ^ 1);
+                if (q == 0) TRACE_AT(cc, 3);
+                tc_fence_after();
+#if !defined(PYMFB_EXP_SKIP_CONVERT)
+                const float* xs = reinterpret_cast<const float*>(smem_gen + s * Cfg::STAGE_BYTES);
+                float v[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = xs[r * TILE_COLS + mylane];
+                park_hilo(lane_addr + t * 64, v);
+                tmem_st_wait();
+#endif
+                tc_fence_before();
+                __syncwarp();
+                if (q == 0) TRACE_AT(cc, 4);
+                if (lane == 0) mbar_arrive(afull_bar(t));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (++t == Cfg::NT) { t = 0; tph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int nsegC = (nd + segc - 1) / segc;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            float creg[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) creg[j] = 0.f;
+            // Old H of this lane's column, fetched NOW: under a saturated memory system a dependent
+            // global load takes ~3 us, and doing it after the last segment stalled every tile by ~10 us.
+            const int col = tile * TILE_COLS + q * 32 + lane;
+            // KP = 64 sits at the register cap of this kernel (168): holding the old H column (64 values) next to
+            // the 64 sums through the whole tile made the compiler spill and cost the pass 20 % once the centering
+            // terms were added (same-box bisect).  LEAN: the column is pulled into L2 when the last W^T X segment
+            // starts, summed (and thereby pulled into L1) while the G H MMAs are in flight, and re-read 16 values at a time.
+            constexpr bool LEAN = (KP == 64);
+            float hreg[LEAN ? 1 : KP];
+            float xs = 0.f;
+            if constexpr (!LEAN) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) hreg[j] = (col < n_loc) ? __ldg(Hc + (int64_t)j * ldh + col) : 0.f;
+                xs = (wmean != nullptr && col < n_loc) ? __ldg(xsum + col) : 0.f;
+            }
+            for (int seg = 0; seg < nsegC; ++seg, ++g) {
+                if constexpr (LEAN) {
+                    if (seg == nsegC - 1 && col < n_loc) {
+#pragma unroll 8
+                        for (int j = 0; j < KP; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(Hc + (int64_t)j * ldh + col));
+                        if (wmean != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(xsum + col));
+                    }
+                }
+                const uint32_t b = g & 1u;
+                if (q == 0) TRACE_AT(g * segc, 10);
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                if (q == 0) TRACE_AT(g * segc, 11);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+#pragma unroll
+                    for (int ch = 0; ch < Cfg::NCHAIN; ++ch) {
+                        float hi[16], sm[16];
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + j0, hi);
+                        tmem_ld16(taddr + ch * Cfg::CHAIN_COLS + KP + j0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) creg[j0 + j] += hi[j] + sm[j];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (q == 0) TRACE_AT(g * segc, 12);
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+            }
+            {
+                float hsum = 0.f;                     // column sum of the old H tile (for the centered G H)
+                if constexpr (LEAN) {
+                    if (col < n_loc) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += __ldg(Hc + (int64_t)j * ldh + col);
+                        if (wmean != nullptr) xs = __ldg(xsum + col);
+                    }
+                } else {
+                    if (wmean != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) hsum += hreg[j];
+                    }
+                }
+                const uint32_t b = g & 1u;
+                mbar_wait(tfull_bar(b), (g >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + b * Cfg::SEG_COLS;
+#pragma unroll
+                for (int j0 = 0; j0 < KP; j0 += 16) {
+                    float dh[16], dl[16];
+                    tmem_ld16(taddr + j0, dh);
+                    tmem_ld16(taddr + KP + j0, dl);
+                    tmem_ld_wait();
+                    if (Cfg::NCHAIN > 1) {
+                        float eh[16], el[16];
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + j0, eh);
+                        tmem_ld16(taddr + Cfg::CHAIN_COLS + KP + j0, el);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { dh[j] += eh[j]; dl[j] += el[j]; }
+                    }
+                    if (dbg != nullptr && tile == 0) {
+                        float* o = dbg + (size_t)(q * 32 + lane) * (2 * KP) + j0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { o[j] = creg[j0 + j]; o[KP + j] = dh[j] + dl[j]; }
+                    }
+#if defined(PYMFB_EXP_SKIP_EPI_GLOBAL)
+                    if (col < -1) {
+#else
+                    if (col < n_loc) {
+#endif
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int64_t o = (int64_t)(j0 + j) * ldh + col;
+                            float h;
+                            if constexpr (LEAN) h = __ldg(Hc + o); else h = hreg[j0 + j];
+                            float cj = creg[j0 + j], dj = dh[j] + dl[j];
+#if !defined(PYMFB_TS_NO_CENTER)
+                            if (wmean != nullptr) {
+#if defined(PYMFB_MEAN_LDG)
+                                cj = fmaf(__ldg(wmean + j0 + j), xs, cj);
+                                dj = fmaf(__ldg(gmean + j0 + j), hsum, dj);
+#else
+                                cj = fmaf(s_mean[j0 + j], xs, cj);
+                                dj = fmaf(s_mean[KP + j0 + j], hsum, dj);
+#endif
+                            }
+#endif
+                            const float hn = (Dp != nullptr) ? snmf_ratio(h, cj, Dp[o], Dn[o]) : mu_ratio(h, cj, dj, lam);
+                            const float hh = __uint_as_float(__float_as_uint(hn) & 0xFFFFE000u);
+                            Hn[o] = hn;                                  // new H
+                            Hs[hs_index((j0 + j), col, 2 * KP)] = hh;        // [H_hi ; H_lo] rows for the X.H^T pass
+                            Hs[hs_index(KP + (j0 + j), col, 2 * KP)] = hn - hh;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(b));
+                ++g;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------
 // TS H-update, RS rows per stage (round 2b).  What the commit / MMA-group probe (tests/commit_probe.cu) and the
 // PYMFB_TRACE timeline say about the 32-row kernel above at k = 64: its 8 MMAs per stage are short (64 + 32 tensor
@@ -2128,6 +2454,8 @@ inline int ts_set_attrs() {
     e = cudaFuncSetAttribute(tc::k_h_update_tsr<KP, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsrCfg<KP, 64>::SMEM_BYTES);
     if (e != cudaSuccess) return 1;
     e = cudaFuncSetAttribute(tc::k_h_update_tsr<KP, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsrCfg<KP, 32>::SMEM_BYTES);
+    if (e != cudaSuccess) return 1;
+    e = cudaFuncSetAttribute(tc::k_h_update_ts2w<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TsCfg<KP>::SMEM_BYTES);
     return e == cudaSuccess ? 0 : 1;
 }
 
@@ -2355,6 +2683,12 @@ inline void ts_launch_h(TcPlan& p, const DevState* st, int hsrc, float* Hn, cuda
         tc::k_h_update_tsr<KP, 64><<<grid, tc::TsrCfg<KP, 64>::THREADS, tc::TsrCfg<KP, 64>::SMEM_BYTES, stream>>>(
             p.mapX_p64, p.mapW64, p.mapH_p64[hsrc], p.mapG64, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg,
             std::max(1, p.seg_c / 2), p.lam_h, p.Dp, p.Dn, p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
+        return;
+    }
+    if (p.ts_rs == 2) {
+        tc::k_h_update_ts2w<KP><<<grid, tc::TsCfg<KP>::THREADS, tc::TsCfg<KP>::SMEM_BYTES, stream>>>(
+            p.mapX_p, p.mapW, p.mapH_p[hsrc], p.mapG, st, p.Hbuf[hsrc], Hn, p.Hs[hsrc ^ 1], p.ldh, (int)p.d, (int)p.n_loc, p.h_tiles, p.dbg, p.seg_c, p.lam_h, p.Dp, p.Dn,
+            p.center ? p.wmean : nullptr, p.gmean, p.xsum, p.xsh);
         return;
     }
     if (p.ts_rs == 32) {

@@ -10,7 +10,7 @@
 using namespace pymfb;
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
-__global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups, int waits, long long* out, int ts, int nbig) {
+__global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups, int waits, long long* out, int ts, int nbig, int pattern) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -38,11 +38,16 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n, int ncommit, int groups
 #pragma unroll 8
                     for (int i = 0; i < n; ++i) {
                         const uint64_t ad = tc::make_desc(a_addr + (i & 3) * 32, 16, 1024), bd = tc::make_desc(b_addr + (i & 3) * 32, 16, 1024);
+                        // pattern 0: wide / narrow MMAs alternate, the narrow one accumulates into the upper half of the wide one's columns
+                        //         1: the same, but the narrow MMA has its own columns (no accumulator range shared by consecutive MMAs)
+                        //         2: four wide MMAs, then four narrow ones (overlapping columns as in 0)
+                        const bool narrow = pattern == 2 ? ((i >> 2) & 1) : (i & 1);
+                        const uint32_t dn = pattern == 1 ? tmem + nbig : tmem + nbig / 2;
                         if (ts) {
-                            if (i & 1) tc::umma_tf32_ts(tmem + nbig / 2, tmem + 448 + (i & 3) * 8, bd, id128, 1u);
-                            else tc::umma_tf32_ts(tmem, tmem + 416 + (i & 3) * 8, bd, id256, 1u);
+                            if (narrow) tc::umma_tf32_ts(dn, tmem + 480 + (i & 3) * 8, bd, id128, 1u);
+                            else tc::umma_tf32_ts(tmem, tmem + 448 + (i & 3) * 8, bd, id256, 1u);
                         } else {
-                            if (i & 1) tc::umma_tf32(tmem + nbig / 2, ad, bd, id128, 1u);
+                            if (narrow) tc::umma_tf32(dn, ad, bd, id128, 1u);
                             else tc::umma_tf32(tmem, ad, bd, id256, 1u);
                         }
                     }
@@ -67,19 +72,17 @@ int main() {
     long long* dout; CHECK(cudaMalloc(&dout, 64));
     const int smem = 16384 + 32768 + 2048;
     CHECK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int groups = 2048;
-    for (int ts : {0, 1})
+    const int groups = 1024;
+    for (int ts : {1, 0})
         for (int nbig : {256, 128, 64})
-            for (int waits : {0, 1})
-                for (int n : {4, 8, 16, 32})
-                    for (int nc : {0, 1, 2}) {
-                        if (ts == 0 && nbig != 256) continue;
-                        k_probe<<<148, 128, smem>>>(n, nc, groups, waits, dout, ts, nbig);
-                        CHECK(cudaDeviceSynchronize());
-                        long long cyc = 0;
-                        CHECK(cudaMemcpy(&cyc, dout, sizeof(cyc), cudaMemcpyDeviceToHost));
-                        printf("%s N %3d/%3d waits %d  MMAs/group %2d  commits/group %d : %7.1f cycles/group  (tensor time %d)\n", ts ? "TS" : "SS", nbig, nbig / 2,
-                               waits, n, nc, (double)cyc / groups, n / 2 * (nbig / 2 + nbig / 4));
-                    }
+            for (int pattern : {0, 1, 2}) {
+                const int n = 32;
+                k_probe<<<148, 128, smem>>>(n, 0, groups, 0, dout, ts, nbig, pattern);
+                CHECK(cudaDeviceSynchronize());
+                long long cyc = 0;
+                CHECK(cudaMemcpy(&cyc, dout, sizeof(cyc), cudaMemcpyDeviceToHost));
+                printf("%s N %3d/%3d pattern %d : %6.1f cycles / MMA  (nominal %.1f)\n", ts ? "TS" : "SS", nbig, nbig / 2, pattern,
+                       (double)cyc / groups / n, (nbig / 2 + nbig / 4) / 2.0);
+            }
     return 0;
 }
