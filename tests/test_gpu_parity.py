@@ -518,6 +518,31 @@ def test_cta_pair_h_update_kernel_is_bit_identical(shape, monkeypatch):
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(1024, 128 * 33, 64), (700, 128 * 9 + 5, 20), (2048 + 40, 128 * 12, 32)])
+def test_ts_h_update_kernel_variants_are_bit_identical(shape, monkeypatch):
+    """The TS H-update kernels (k <= 64) exist in four schedules - 32-row stages with separate commits (PYMFB_TS_RS=1, the
+    k = 64 default), two MMA-issuing warps (2), 32- and 64-row stages with one commit per stage (32 / 64; 64 is the
+    k <= 32 default).  They issue the same MMAs in the same order over the same segments, so H after one update and the
+    errors of two further iterations must be bit-identical - ragged d (rows beyond the matrix are zero-filled by TMA),
+    ragged n, k below the padded width."""
+    d, n, k = shape
+    out = []
+    for rs in ("1", "2", "32", "64"):
+        monkeypatch.setenv("PYMFB_TS_RS", rs)
+        e = pymf_b200.Engine(d, n, k, path="tc")
+        try:
+            e.gen_x(1); e.gen_w(2); e.gen_h(3)
+            e.run(1, compute_w=False, compute_h=True, compute_err=False, early_stop=False)
+            H = e.get_h(np.float32)
+            f, _ = e.run(2, early_stop=False)
+            out.append((H, f))
+        finally:
+            e.close()
+    for o in out[1:]:
+        np.testing.assert_array_equal(out[0][0], o[0])
+        np.testing.assert_array_equal(out[0][1], o[1])
+
+
 @pytest.mark.parametrize("shape,path", [((1000, 500, 10), "simt"), ((512, 4096, 32), "tc"), ((1024, 4096, 128), "tc"),
                                         ((300, 3000, 40), "tc")])
 def test_runs_are_bit_reproducible(shape, path):
