@@ -2347,6 +2347,7 @@ struct TcPlan {
     int hh_tasks = 0, hh_cols_per_task = 0;
     bool use_ts = false;             // k <= 64: A operand from TMEM (k_*_ts), else both operands in smem
     bool use_ts2 = false;            // EXPERIMENT (PYMFB_TS2=1, kp = 64): CTA-pair H-update kernel (kernels_ts2.cuh)
+    bool use_tc2 = false;            // EXPERIMENT (PYMFB_TC2=1, 128-wide blocks of bases): CTA-pair SS H-update kernel (kernels_tc2.cuh)
     int h_tiles = 0, x_rb = 0, x_cols_per_task = 0, x_tasks = 0;
     float* dbg = nullptr;      // optional raw-accumulator dump (tests/tc_probe.cu)
     const float* Dp = nullptr; // Semi-NMF: G+ H and G- H of the H buffer being updated (set by the scheduler), else null

@@ -37,6 +37,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_ts2.cuh"
+#include "kernels_tc2.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_svd.cuh"
 
@@ -272,6 +273,7 @@ static int plan_tc(pymfb_ctx* c) {
     if (tc_plan(c->tc, c->device, c->sm_count, c->d, c->n_loc, c->k, c->kp, c->X, c->ldx, c->ldh, c->H[0], c->H[1], c->xps, c->xsh))
         return fail("tcgen05 plan failed: %s", c->tc.err.c_str());
     if (ts2_prepare(c->tc)) return fail("CTA-pair kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (tc2_prepare(c->tc)) return fail("CTA-pair SS kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     fused_release(c->fused);
     if (fused_wanted(c->tc) && fused_plan(c->fused, c->tc)) return fail("fused-kernel plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
@@ -377,6 +379,8 @@ static int launch_h_update(pymfb_ctx* c) {
         }
         if (c->tc.use_ts2) {
             if (ts2_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("CTA-pair H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (c->tc.use_tc2) {
+            if (tc2_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("CTA-pair SS H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (tc_h_update(c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->stream, &c->launches)) return fail("tcgen05 H-update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         dim3 grid((unsigned)((c->n_loc + TILE_N - 1) / TILE_N), (unsigned)(c->kp / c->kb), (unsigned)c->hsplit);

@@ -518,6 +518,31 @@ def test_cta_pair_h_update_kernel_is_bit_identical(shape, monkeypatch):
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(1024, 128 * 33, 128), (700, 128 * 9 + 5, 100), (2048, 128 * 100 + 17, 256)])
+def test_cta_pair_ss_h_update_kernel_is_bit_identical(shape, monkeypatch):
+    """Opt-in CTA-pair SS H-update kernel (PYMFB_TC2=1, kernels_tc2.cuh; 128-wide blocks of bases): one tcgen05.mma.cta_group::2
+    covers the tiles of both CTAs with the same per-tile MMA chain as k_h_update_tc, so one H update must be bit-identical -
+    odd tile count (virtual out-of-bounds tile), ragged n and d, k below the padded width, two blocks of bases."""
+    d, n, k = shape
+    out = []
+    for tc2 in (False, True):
+        if tc2:
+            monkeypatch.setenv("PYMFB_TC2", "1")
+        else:
+            monkeypatch.delenv("PYMFB_TC2", raising=False)
+        e = pymf_b200.Engine(d, n, k, path="tc")
+        try:
+            e.gen_x(1); e.gen_w(2); e.gen_h(3)
+            e.run(1, compute_w=False, compute_h=True, compute_err=False, early_stop=False)
+            H = e.get_h(np.float32)
+            f, _ = e.run(2, early_stop=False)
+            out.append((H, f))
+        finally:
+            e.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("shape", [(1024, 128 * 33, 64), (700, 128 * 9 + 5, 20), (2048 + 40, 128 * 12, 32)])
 def test_ts_h_update_kernel_variants_are_bit_identical(shape, monkeypatch):
     """The TS H-update kernels (k <= 64) exist in four schedules - 32-row stages with separate commits (PYMFB_TS_RS=1, the
