@@ -329,6 +329,30 @@ def test_tensor_core_path_matches_fp32_path(shape):
     assert rel(res["tc"][1], res["simt"][1]) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(512, 4096 + 40, 32), (1000, 2000, 64), (700, 1157, 50)])
+def test_ss_kernels_serve_small_k_when_forced(shape, monkeypatch):
+    """The SS kernels (both operands from shared memory, three rings; the k >= 96 default) also instantiate for 32 and 64 bases
+    (PYMFB_TC_FORCE_SS=1, used for A/B runs against the TS kernels): float64 oracle parity over 5 iterations."""
+    d, n, k = shape
+    monkeypatch.setenv("PYMFB_TC_FORCE_SS", "1")
+    rng = np.random.RandomState(d + n + k)
+    X = rng.random_sample((d, n)).astype(np.float32)
+    W0 = rng.random_sample((d, k))
+    H0 = rng.random_sample((k, n))
+    Wr, Hr = W0.copy(), H0.copy()
+    fr = O.factorize(X.astype(np.float64), Wr, Hr, niter=5, early_stop=False)
+    e = pymf_b200.Engine(d, n, k, path="tc")
+    try:
+        e.set_err_mode("trace")
+        e.upload_x(X); e.set_w(W0); e.set_h(H0)
+        f, _ = e.run(5, early_stop=False)
+        W, H = e.get_w(), e.get_h()
+    finally:
+        e.close()
+    assert rel(W, Wr) < TOL_WH and rel(H, Hr) < TOL_WH
+    assert np.max(np.abs(f - fr) / fr) < TOL_FERR
+
+
 @pytest.mark.parametrize("shape", [(512, 4096, 32), (1000, 5000, 20), (4096, 8192, 32), (300, 1100, 32)])
 def test_fused_one_pass_kernel_matches_two_pass(shape, monkeypatch):
     """kernels_fused.cuh (H update + X.H^T + H.H^T with X read once) vs the two-pass tensor-core
