@@ -12,6 +12,7 @@
 //   AB <- allreduce(P)                         NCCL (world > 1)
 //   ferr_i = sqrt(xx - 2<W,A> + <G,B>)         k_err (fp64), device-side stop flag
 #include <cuda_runtime.h>
+#include <chrono>
 #include <dlfcn.h>
 #include <immintrin.h>
 #include <stdarg.h>
@@ -1182,12 +1183,24 @@ int pymfb_upload_x(pymfb_ctx* c, const void* x_host, int dtype, int64_t ld) {
     if (ld < c->n_loc) return fail("leading dimension too small");
     if (dtype != PYMFB_F32 && dtype != PYMFB_F64) return fail("bad dtype %d", dtype);
     CU(cudaSetDevice(c->device));
+    static const bool tlog = getenv("PYMFB_UPLOAD_LOG") != nullptr;      // experiment: phase times of the ingest on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     CK(ensure_own_x(c));
+    if (tlog) CU(cudaStreamSynchronize(c->stream));
+    const auto t1 = std::chrono::steady_clock::now();
     c->last_upload_pinned = host_is_pinned(x_host);
     if (c->last_upload_pinned) CK(pinned_upload(c, x_host, dtype, ld));
     else CK(staged_upload(c, x_host, dtype, ld));
     CU(cudaStreamSynchronize(c->stream));
-    return data_changed(c);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = data_changed(c);
+    if (tlog) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "[pymfb] upload_x: allocate + clear %.3f s, transfer %.3f s (%s), after %.3f s\n", sec(t0, t1), sec(t1, t2),
+                c->last_upload_pinned ? "direct DMA" : "staged", sec(t2, t3));
+    }
+    return rc;
 }
 
 int pymfb_last_upload_pinned(pymfb_ctx* c) { return c && c->last_upload_pinned ? 1 : 0; }
