@@ -274,6 +274,9 @@ constexpr int TRACE_STAGES = 4096;
 #endif
 
 constexpr int SEG_STAGES = 8;         // stages per accumulation segment (see "segments" below)
+#ifndef PYMFB_SS_SEG_X
+#define PYMFB_SS_SEG_X 8               // the same for the X H^T / H H^T passes of the SS kernels (run-time: PYMFB_SEG_X)
+#endif
 
 // Segments.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, so a chain of n
 // accumulating MMAs over positive data comes out LOW by ~4.2e-8 * n relative (measured: 2.7e-5 after
@@ -682,7 +685,8 @@ __global__ void __launch_bounds__(XCfg<KP>::THREADS, 1)
 k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
          const DevState* __restrict__ st, float* __restrict__ P, int d, int n_loc,
          int cols_per_task, int num_rb, int num_tasks, float* __restrict__ dbg, int ldp,
-         float* __restrict__ Ppart, int64_t part_stride, int xsh, int xrev, int pf) {
+         float* __restrict__ Ppart, int64_t part_stride, int xsh, int xrev, int pf, int seg_x) {
+    // seg_x: stages per accumulation segment (X H^T and H H^T launches must use the same value, see "Segments")
     // ldp: row stride of P (= padded k of the whole problem; P points at this launch's block of columns)
     // Ppart != nullptr: deterministic combine of the column splits - every task stores its sums in copy (task / num_rb)
     // of P's layout (part_stride floats apart) and k_sum_copies adds the copies in split order into P afterwards.
@@ -780,7 +784,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 const int nch = task_chunks(task, c_begin);
                 int ch = 0;
                 while (ch < nch) {
-                    const int seg_end = min(ch + SEG_STAGES, nch);
+                    const int seg_end = min(ch + seg_x, nch);
                     const uint32_t b = g & 1u;
                     mbar_wait(bar.tempty(b), ((g >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -853,7 +857,7 @@ k_xht_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         for (int task = blockIdx.x; task < num_tasks; task += gridDim.x) {
             int c_begin;
             const int nch = task_chunks(task, c_begin);
-            const int nseg = (nch + SEG_STAGES - 1) / SEG_STAGES;
+            const int nseg = (nch + seg_x - 1) / seg_x;
             float areg[Cfg::NJ];
 #pragma unroll
             for (int j = 0; j < Cfg::NJ; ++j) areg[j] = 0.f;
@@ -2365,6 +2369,7 @@ struct TcPlan {
     int xrev = 0;              // experiment (PYMFB_XREV=1): the X H^T pass walks the column ranges backwards, hoping to find the
                                // tail of the H-update pass in L2 - measured neutral on cfg2 / cfg3 / cfg4 k=64, so off
     int seg_c = 1;             // stages per segment of the W^T X contraction (= kp / 32: the G H chain length)
+    int seg_x = 8;             // stages per segment of the X H^T / H H^T contractions (SS kernels: PYMFB_SEG_X; TS kernels: SEG_STAGES)
     float lam_h = 0.f;         // BNMF penalty weight of the next H-update launch (0 = plain NMF), set by the scheduler
     std::string err;
 };
@@ -2608,7 +2613,9 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     splits = std::min(splits, chunks);
     // Column ranges are whole segments (SEG_STAGES stages) wherever n allows, for X H^T and H H^T alike: the W update
     // is the ratio A / (W B), so the accumulation chains of A and B must have the same length (see "Segments").
-    auto seg_round = [&](int64_t per) { return (per >= tc::SEG_STAGES) ? (per + tc::SEG_STAGES - 1) / tc::SEG_STAGES * tc::SEG_STAGES : per; };
+    { const char* e = getenv("PYMFB_SEG_X"); p.seg_x = (!p.use_ts && e && atoi(e) > 0) ? atoi(e) : (p.use_ts ? tc::SEG_STAGES : PYMFB_SS_SEG_X); }
+    const int64_t segx = p.seg_x;
+    auto seg_round = [&](int64_t per) { return (per >= segx) ? (per + segx - 1) / segx * segx : per; };
     const int64_t chunks_per = seg_round((chunks + splits - 1) / splits);
     p.x_cols_per_task = (int)(chunks_per * 32);
     splits = (chunks + chunks_per - 1) / chunks_per;
@@ -2616,7 +2623,7 @@ inline int tc_plan(TcPlan& p, int device, int sm_count, int64_t d, int64_t n_loc
     {   // H H^T tasks (TS kernels): ~one short task per SM, never shorter than the X H^T chains
         int64_t hsplits = std::min<int64_t>(chunks, sm_count);
         int64_t hper = seg_round((chunks + hsplits - 1) / hsplits);
-        if (hper < tc::SEG_STAGES) hper = std::min<int64_t>(chunks_per, tc::SEG_STAGES);
+        if (hper < segx) hper = std::min<int64_t>(chunks_per, segx);
         p.hh_cols_per_task = (int)(hper * 32);
         p.hh_tasks = (int)((chunks + hper - 1) / hper);
     }
@@ -2734,7 +2741,7 @@ inline void tc_launch_x(TcPlan& p, const DevState* st, int hsrc, float* P, cudaS
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapX_x, p.mapH_xb[hsrc][b], st, P + b * p.kpb, (int)p.d, (int)p.n_loc, p.x_cols_per_task, p.x_rb, p.x_tasks,
-            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh, p.xrev, p.ss_pf);
+            p.dbg, p.kp, p.xpart ? p.xpart + b * p.kpb : nullptr, (int64_t)p.d * p.kp, p.xsh, p.xrev, p.ss_pf, p.seg_x);
 }
 // true when the launch also produced H H^T (so the caller skips its own H H^T kernel): the TS kernels run it as
 // extra tasks of the same launch, the SS kernels as a second launch with H itself as the streamed operand
@@ -2748,7 +2755,7 @@ inline void tc_launch_hht(TcPlan& p, const DevState* st, int hsrc, float* PB, cu
     for (int b = 0; b < p.nblk; ++b)
         tc::k_xht_tc<KP><<<grid, tc::XCfg<KP>::THREADS, tc::XCfg<KP>::SMEM_BYTES, stream>>>(
             p.mapH_a[hsrc], p.mapH_xb[hsrc][b], st, PB + b * p.kpb, p.kp, (int)p.n_loc, p.hh_cols_per_task, hh_rb, ntasks,
-            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel, 0, 0);
+            nullptr, p.kp, p.xpartB ? p.xpartB + b * p.kpb : nullptr, (int64_t)p.kp * p.kp, tc::kNoPanel, 0, 0, p.seg_x);
 }
 inline int tc_xht(TcPlan& p, const DevState* st, const float* Hc, float* P, cudaStream_t stream, int64_t* launches) {
     const int hsrc = (Hc == p.Hbuf[0]) ? 0 : 1;
