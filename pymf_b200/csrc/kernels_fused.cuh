@@ -65,6 +65,8 @@ struct FusedParams {
     const float* Rg;        // H / (G H + 1e-9) of the OLD H (kp x ldh), from k_gh_ratio
     float* PA;              // d x kp   (+= X Hn^T)
     float* PB;              // kp x kp  (+= Hn Hn^T)
+    float* PartA;           // deterministic flush: ngroups copies of A (d x kp each), copy g written by the CTAs of group g; null = atomics
+    float* PartB;           // gridDim.x copies of B (kp x kp), one per CTA
     float* Cpart;           // [ngroups][nslot][kp][128] fp32 accumulators of the slab partials (zero between uses)
     int* tile_cnt;          // [n_tiles] slabs arrived
     int* tile_done;         // [n_tiles] 1 once Hn / Hs of the tile are visible
@@ -550,16 +552,28 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
         for (int rb = 0; rb < 2; ++rb) {
             const int row = row_slab + rb * 128 + et;
             if (row < p.d) {
-                float* dst = p.PA + (int64_t)row * KP;
                 const float* acc = pacc + rb * (KP * 128) + et;
+                if (p.PartA != nullptr) {              // this group's copy of A: k_sum_copies adds the copies in group order
+                    float* dst = p.PartA + (size_t)seq.g * p.d * KP + (int64_t)row * KP;
 #pragma unroll
-                for (int j = 0; j < KP; ++j) atomicAdd(dst + j, acc[j * 128]);
+                    for (int j = 0; j < KP; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j * 128], acc[(j + 1) * 128], acc[(j + 2) * 128], acc[(j + 3) * 128]);
+                } else {
+                    float* dst = p.PA + (int64_t)row * KP;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) atomicAdd(dst + j, acc[j * 128]);
+                }
             }
         }
         if (et < KP) {
-            float* dst = p.PB + (int64_t)et * KP;
+            if (p.PartB != nullptr) {
+                float* dst = p.PartB + (size_t)blockIdx.x * KP * KP + (int64_t)et * KP;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) atomicAdd(dst + j, phh[j * KP + et]);
+                for (int j = 0; j < KP; ++j) dst[j] = phh[j * KP + et];
+            } else {
+                float* dst = p.PB + (int64_t)et * KP;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) atomicAdd(dst + j, phh[j * KP + et]);
+            }
         }
     } else if (warp < F_UPD_WARP0) {
         // ===== publisher warps: fence (covers the epilogue warps' REDs: they happen-before through the
@@ -660,6 +674,8 @@ k_fused_ts(const __grid_constant__ CUtensorMap mapXp,   // X, plain boxes 128 co
 struct FusedPlan {
     bool ready = false;
     float* Cpart = nullptr;
+    float* Part = nullptr;       // deterministic flush: ngroups copies of A, then one copy of B per CTA
+    bool zero_p = true;          // atomics flush: P must be cleared before the launch
     float* Rg = nullptr;         // kp x ldh
     int* cnt = nullptr;          // [n_tiles] arrival counters, [n_tiles] done flags
     int n_tiles = 0, nslab = 0, ngroups = 0, depth = 2, nslot = 4, hint = 1, pf = 1;
@@ -668,19 +684,25 @@ struct FusedPlan {
 
 inline void fused_release(FusedPlan& f) {
     if (f.Cpart) cudaFree(f.Cpart);
+    if (f.Part) cudaFree(f.Part);
+    f.Part = nullptr;
     if (f.Rg) cudaFree(f.Rg);
     if (f.cnt) cudaFree(f.cnt);
     f.Cpart = nullptr; f.Rg = nullptr; f.cnt = nullptr; f.ready = false;
 }
 
-// PYMFB_FUSED=1 enables the one-pass kernel for k <= 32 shapes whose row slabs fit the grid
-// (d <= 256 x #SMs); PYMFB_FUSED_DEPTH (default 3) and PYMFB_FUSED_HINT (default 1) tune it.
+// The one-pass kernel serves k <= 32 shapes whose row slabs fit the grid (d <= 256 x #SMs).  It is the DEFAULT where it
+// wins: d <= 256, i.e. one row slab - a column tile is then owned by ONE CTA, nothing is reduced across CTAs, and the
+// kernel beats the two passes (256 x 4M, k = 32: 2.49 vs 2.91 ms per iteration; at d = 512 they tie, above the two passes
+// win).  PYMFB_FUSED=1 forces it for every eligible shape, =0 disables it; PYMFB_FUSED_DEPTH (default 3)
+// and PYMFB_FUSED_HINT (default 1) tune it.
 inline bool fused_wanted(const TcPlan& p) {
     if (!p.ready || !p.use_ts || p.kp != tc::F_KP) return false;
     const int nslab = (int)((p.d + tc::F_SLAB - 1) / tc::F_SLAB);
     if (nslab > p.sm_count) return false;
     const char* e = getenv("PYMFB_FUSED");
-    return e && e[0] == '1';
+    if (e) return e[0] == '1';
+    return nslab == 1 && p.h_tiles >= 2 * p.sm_count;
 }
 
 inline int fused_plan(FusedPlan& f, const TcPlan& p) {
@@ -698,6 +720,13 @@ inline int fused_plan(FusedPlan& f, const TcPlan& p) {
     if (cudaMemset(f.Cpart, 0, cbytes) != cudaSuccess) return 1;
     if (cudaMalloc(&f.Rg, (size_t)p.kp * p.ldh * sizeof(float)) != cudaSuccess) return 1;
     if (cudaMalloc(&f.cnt, (size_t)2 * f.n_tiles * sizeof(int)) != cudaSuccess) return 1;
+    {   // deterministic flush (bit-reproducible W, as on the two-pass kernels) while the copies stay small
+        const size_t pbytes = ((size_t)f.ngroups * p.d * p.kp + (size_t)f.ngroups * f.nslab * p.kp * p.kp) * sizeof(float);
+        const char* e = getenv("PYMFB_DETERMINISTIC");
+        const bool want = e ? e[0] == '1' : pbytes <= ((size_t)1 << 30);
+        if (want) { if (cudaMalloc(&f.Part, pbytes) != cudaSuccess) return 1; }
+        f.zero_p = f.Part == nullptr;
+    }
     using Cfg = tc::TsCfg<tc::F_KP>;
     f.smem = tc::F_STAGES * Cfg::STAGE_BYTES + (tc::F_PACC_FLOATS + tc::F_PHH_FLOATS) * 4 +
              1024 /*barriers, queue*/ + 1024 /*align*/;
@@ -715,6 +744,7 @@ inline int fused_launch(FusedPlan& f, TcPlan& p, const DevState* st, const float
     tc::k_gh_ratio<<<(unsigned)((p.n_loc + 127) / 128), 128, 0, stream>>>(st, G, Hc, p.ldh, (int)p.n_loc, f.Rg);
     tc::FusedParams fp;
     fp.st = st; fp.Hc = Hc; fp.Hn = Hn; fp.Hs = p.Hs[hdst]; fp.Rg = f.Rg; fp.PA = P; fp.PB = P + p.d * p.kp;
+    fp.PartA = f.Part; fp.PartB = f.Part ? f.Part + (size_t)f.ngroups * p.d * p.kp : nullptr;
     fp.Cpart = f.Cpart; fp.tile_cnt = f.cnt; fp.tile_done = f.cnt + f.n_tiles;
     fp.ldh = p.ldh; fp.d = (int)p.d; fp.n_loc = (int)p.n_loc; fp.n_tiles = f.n_tiles;
     fp.nslab = f.nslab; fp.ngroups = f.ngroups; fp.depth = f.depth; fp.nslot = f.nslot; fp.hint = f.hint;
@@ -728,6 +758,12 @@ inline int fused_launch(FusedPlan& f, TcPlan& p, const DevState* st, const float
     const int grid = f.ngroups * f.nslab;
     tc::k_fused_ts<<<grid, tc::F_THREADS, f.smem, stream>>>(p.mapX_p, p.mapW, p.mapX_x, p.mapH_x[hdst], p.mapH_a[hdst], fp);
     *launches += 2;
+    if (f.Part) {                  // P = sum of the copies, in group / CTA order
+        const int64_t na = p.d * p.kp, nb = (int64_t)p.kp * p.kp;
+        tc::k_sum_copies<<<(unsigned)std::min<int64_t>(((na + nb) / 4 + 255) / 256, 8 * p.sm_count), 256, 0, stream>>>(
+            st, fp.PartA, f.ngroups, na, P, fp.PartB, grid, nb, P + na);
+        *launches += 1;
+    }
     p.hs_valid[hdst] = true;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -409,8 +409,10 @@ static int launch_h_update(pymfb_ctx* c) {
 
 // One-pass iteration body (kernels_fused.cuh): H[hcur] -> H[hcur^1], P = [X H^T | H H^T], AB = allreduce(P)
 static int launch_fused(pymfb_ctx* c) {
-    k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
-    c->launches += 1;
+    if (c->fused.zero_p) {         // atomics flush (no room for the ordered copies): the kernel adds into a cleared P
+        k_zero<<<grid_for(c->ab_count, 256, 8 * c->sm_count), 256, 0, c->stream>>>(c->st, c->P, c->ab_count);
+        c->launches += 1;
+    }
     cudaEvent_t e0, e1;
     CK(timing_begin(c, 0, &e0, &e1));
     if (fused_launch(c->fused, c->tc, c->st, c->H[c->hcur], c->H[c->hcur ^ 1], c->G, c->P, c->stream, &c->launches, fault_buffer()))

@@ -353,10 +353,12 @@ def test_ss_kernels_serve_small_k_when_forced(shape, monkeypatch):
     assert np.max(np.abs(f - fr) / fr) < TOL_FERR
 
 
-@pytest.mark.parametrize("shape", [(512, 4096, 32), (1000, 5000, 20), (4096, 8192, 32), (300, 1100, 32)])
+@pytest.mark.parametrize("shape", [(512, 4096, 32), (1000, 5000, 20), (4096, 8192, 32), (300, 1100, 32),
+                                   (256, 40000, 32), (200, 50001, 20), (64, 131072, 32)])
 def test_fused_one_pass_kernel_matches_two_pass(shape, monkeypatch):
     """kernels_fused.cuh (H update + X.H^T + H.H^T with X read once) vs the two-pass tensor-core
-    kernels vs the float64 oracle; PYMFB_FUSED forces / disables the fused kernel."""
+    kernels vs the float64 oracle; PYMFB_FUSED forces / disables the fused kernel.  d <= 256 (one row slab: the
+    shapes where the one-pass kernel is the default) included."""
     d, n, k = shape
     rng = np.random.RandomState(d + n)
     X = rng.random_sample((d, n)).astype(np.float32)
@@ -593,10 +595,11 @@ def test_ts_h_update_kernel_variants_are_bit_identical(shape, monkeypatch):
 
 
 @pytest.mark.parametrize("shape,path", [((1000, 500, 10), "simt"), ((512, 4096, 32), "tc"), ((1024, 4096, 128), "tc"),
-                                        ((300, 3000, 40), "tc")])
+                                        ((300, 3000, 40), "tc"), ((256, 65536, 32), "tc"), ((150, 40000, 20), "tc")])
 def test_runs_are_bit_reproducible(shape, path):
-    """The column splits of X H^T / H H^T are combined in a fixed order (partial copies + ticket, no atomics), so
-    two runs of the same problem in one process give bit-identical W, H and ferr."""
+    """The column splits of X H^T / H H^T are combined in a fixed order (partial copies, no atomics), so
+    two runs of the same problem in one process give bit-identical W, H and ferr - also on the d <= 256, k <= 32 shapes
+    that run the one-pass kernel by default (one copy of [A | B] per CTA group, summed in group order)."""
     d, n, k = shape
     X = O.gen_matrix(71, d, n)
     W0 = O.gen_matrix(72, d, k).astype(np.float64)
