@@ -40,7 +40,7 @@ def _free_port():
 @pytest.mark.parametrize("shape,path,cls", [((512, 1000, 32), "tc", "NMF"), ((300, 777, 10), "simt", "NMF"),
                                             ((1024, 4096, 128), "tc", "NMF"), ((512, 1000, 32), "tc", "BNMF"),
                                             ((512, 1000, 32), "tc", "SNMF"), ((300, 777, 10), "simt", "SNMF"),
-                                            ((200, 80000, 20), "tc", "NMF")])     # d <= 256, k <= 32: the one-pass kernel per rank
+                                            ((200, 180000, 20), "tc", "NMF")])    # d <= 256, k <= 32, d * n_local > 2^24: the one-pass kernel per rank
 def test_two_gpus_match_oracle(tmp_path, shape, path, cls):
     import torch
     if torch.cuda.device_count() < 2:
